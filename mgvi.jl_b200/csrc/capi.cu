@@ -1,0 +1,581 @@
+// extern "C" surface of libmgvib200 (include/mgvi_b200.h) and the model-independent drivers:
+// Newton-CG with strong-Wolfe line search (src/newtoncg.jl:85-167) and mgvi_step
+// (src/mgvi_impl.jl:129-144).  Scalar control flow runs on the host, every vector operation is a
+// kernel launch on the context's stream.
+#include <math.h>
+#include <functional>
+#include "engine.h"
+
+namespace mgvi {
+void comm_unique_id(uint8_t out[128]);
+void comm_init(mgvib200_ctx* ctx, int rank, int world, const uint8_t id[128]);
+void comm_destroy(mgvib200_ctx* ctx);
+}  // namespace mgvi
+
+using namespace mgvi;
+
+namespace {
+
+thread_local std::string g_last_global_error;
+
+template <typename F>
+int guarded(mgvib200_ctx* ctx, F&& f) {
+    try {
+        f();
+        return MGVIB200_OK;
+    } catch (const RtError& e) {
+        if (ctx) ctx->err = e.msg; else g_last_global_error = e.msg;
+        return e.code ? e.code : MGVIB200_ERR_INVALID;
+    } catch (const std::exception& e) {
+        if (ctx) ctx->err = e.what(); else g_last_global_error = e.what();
+        return MGVIB200_ERR_INVALID;
+    }
+}
+
+void need(bool cond, const char* msg) { if (!cond) throw RtError{msg, MGVIB200_ERR_INVALID}; }
+
+double* stage_in(mgvib200_model* m, int slot, const double* host, size_t count) {
+    m->stage[slot].ensure(sizeof(double) * count);
+    rt_h2d(m->stage[slot].p, host, sizeof(double) * count, m->ctx->stream);
+    return m->stage[slot].as<double>();
+}
+double* stage_out(mgvib200_model* m, int slot, size_t count) {
+    m->stage[slot].ensure(sizeof(double) * count);
+    return m->stage[slot].as<double>();
+}
+
+mgvib200_cg_opts cg_defaults(const mgvib200_cg_opts* o) {
+    mgvib200_cg_opts d;
+    d.abstol = 1.4901161193847656e-08;   // LinearSolve default_tol(Float64) = sqrt(eps)
+    d.reltol = 1.4901161193847656e-08;
+    d.maxiters = 0;
+    if (o) d = *o;
+    return d;
+}
+
+mgvib200_newtoncg_opts ncg_defaults(const mgvib200_newtoncg_opts* o) {
+    mgvib200_newtoncg_opts d;
+    d.alpha = 0.1; d.steps = 4; d.i0 = 5; d.i1 = 50;     // src/newtoncg.jl:14-31
+    if (o) d = *o;
+    return d;
+}
+
+// ----------------------------------------------------------------------------------------------
+// LineSearches.StrongWolfe{Float64}() -- src/newtoncg.jl:30, call :142
+// ----------------------------------------------------------------------------------------------
+typedef std::function<double(double)> Fn1;
+
+double sw_interpolate(double a1, double a2, double f1, double f2, double g1, double g2) {
+    const double d1 = g1 + g2 - 3.0 * (f1 - f2) / (a1 - a2);
+    const double d2 = sqrt(d1 * d1 - g1 * g2);
+    return a2 - (a2 - a1) * ((g2 + d2 - d1) / (g2 - g1 + 2.0 * d2));
+}
+
+double sw_zoom(double a_lo, double a_hi, double dphi0, double phi0, const Fn1& phi, const Fn1& dphi, double c1,
+               double c2) {
+    double a_j = NAN;
+    for (int it = 0; it < 10; ++it) {
+        const double f_lo = phi(a_lo), g_lo = dphi(a_lo);
+        const double f_hi = phi(a_hi), g_hi = dphi(a_hi);
+        if (a_lo < a_hi) a_j = sw_interpolate(a_lo, a_hi, f_lo, f_hi, g_lo, g_hi);
+        else a_j = sw_interpolate(a_hi, a_lo, f_hi, f_lo, g_hi, g_lo);
+        const double f_j = phi(a_j);
+        if (f_j > phi0 + c1 * a_j * dphi0 || f_j > f_lo) {
+            a_hi = a_j;
+        } else {
+            const double g_j = dphi(a_j);
+            if (fabs(g_j) <= -c2 * dphi0) return a_j;
+            if (g_j * (a_hi - a_lo) >= 0.0) a_hi = a_lo;
+            a_lo = a_j;
+        }
+    }
+    return a_j;
+}
+
+void strong_wolfe(const Fn1& phi, const Fn1& dphi, double alpha0, double phi0, double dphi0, double& a_out,
+                  double& f_out) {
+    const double c1 = 1e-4, c2 = 0.9, rho = 2.0, a_max = 65536.0;
+    double a_prev = 0.0, a = alpha0, f_prev = phi0;
+    int i = 1;
+    while (a < a_max) {
+        const double f_a = phi(a);
+        if (f_a > phi0 + c1 * a * dphi0 || (f_a >= f_prev && i > 1)) {
+            a_out = sw_zoom(a_prev, a, dphi0, phi0, phi, dphi, c1, c2);
+            f_out = phi(a_out);
+            return;
+        }
+        const double g_a = dphi(a);
+        if (fabs(g_a) <= -c2 * dphi0) { a_out = a; f_out = f_a; return; }
+        if (g_a >= 0.0) {
+            a_out = sw_zoom(a, a_prev, dphi0, phi0, phi, dphi, c1, c2);
+            f_out = phi(a_out);
+            return;
+        }
+        a_prev = a; a *= rho; f_prev = f_a; ++i;
+    }
+    a_out = a_max;
+    f_out = phi(a_max);
+}
+
+// ----------------------------------------------------------------------------------------------
+// MGVI._optimize(f, adsel, Sigma_bar_inv, x0, ::NewtonCG, opts) -- src/newtoncg.jl:85-167
+// All pointers device.  x_out may alias nothing else.
+// ----------------------------------------------------------------------------------------------
+struct NewtonWs {
+    DevBuf x, g, trial, gt;
+    ReduceWs rws;
+    void release() { x.release(); g.release(); trial.release(); gt.release(); rws.partials.release(); rws.counters.release(); rws.red.release(); }
+};
+
+void newtoncg_dev(mgvib200_model* m, const double* x0, const double* R, int64_t n,
+                  const mgvib200_newtoncg_opts& o, double* x_out, double* f_out, mgvib200_newtoncg_trace* tr_out) {
+    Engine* E = m->eng;
+    mgvib200_ctx* ctx = m->ctx;
+    const long long N = E->n_theta;
+    need(o.steps >= 0 && o.steps <= MGVIB200_TRACE_MAX, "NewtonCG: steps must be in [0, 64]");
+    static thread_local NewtonWs ws;
+    const size_t b = sizeof(double) * N;
+    ws.x.ensure(b); ws.g.ensure(b); ws.trial.ensure(b); ws.gt.ensure(b);
+    double* x = ws.x.as<double>();
+    double* g = ws.g.as<double>();
+    double* trial = ws.trial.as<double>();
+    double* gt = ws.gt.as<double>();
+    mgvib200_newtoncg_trace tr;
+    memset(&tr, 0, sizeof tr);
+    rt_event_record(ctx->ev0, ctx->stream);
+
+    auto f = [&](const double* xp) { tr.f_calls++; return E->kl_value_grad(xp, R, n, nullptr); };
+    auto gradf = [&](const double* xp, double* gout) { tr.g_calls++; E->kl_value_grad(xp, R, n, gout); };
+
+    rt_d2d(x, x0, b, ctx->stream);
+    double f_prev = f(x);                                  // :106
+    tr.initial_f = f_prev;
+    tr.f_history[0] = f_prev;
+    tr.cg_iterations[tr.n_cg_iterations++] = o.i0;         // :108
+    double f_n = 0.0, df_n = 0.0;
+    for (int64_t step = 1; step <= o.steps; ++step) {      // :112
+        gradf(x, g);                                       // :115
+        E->mean_metric_prepare(x, R, n);                   // Sigma_bar_inv(x_n), :120 / mgvi_impl.jl:137-138
+        E->ncg_init(g);
+        int64_t k = 0;
+        if (step == 1) {                                   // :121-127
+            while (E->ncg_active()) {
+                E->ncg_update(); ++k;
+                if (k >= o.i0) break;
+            }
+        } else {                                           // :129-139
+            double f_km1 = f_prev;
+            while (E->ncg_active()) {
+                E->ncg_update(); ++k;
+                vec_axpy(ctx, ws.rws, trial, x, -1.0, E->ncg_dx(), N);
+                const double f_k = f(trial);
+                if (k >= o.i1 || fabs(f_k - f_km1) < o.alpha * df_n) {
+                    tr.cg_iterations[tr.n_cg_iterations++] = k;
+                    break;
+                }
+                f_km1 = f_k;
+            }
+        }
+        tr.cg_updates[step - 1] = k;
+        const double* dx = E->ncg_dx();
+        if (k == 0) {
+            // the iterator yielded nothing: dx = 0 (cg_iterator! zeroes it)
+            static thread_local DevBuf zero;
+            zero.ensure(b);
+            rt_memset(zero.p, 0, b, ctx->stream);
+            dx = zero.as<double>();
+        }
+        // line search along d = -dx (linesearch_args, :64-71): phi(a) = f(x + a d), phi'(a) = grad f(x + a d) . d
+        const double dphi0 = -vec_dot(ctx, ws.rws, g, dx, N);
+        Fn1 phi = [&](double a) {
+            vec_axpy(ctx, ws.rws, trial, x, -a, dx, N);
+            return f(trial);
+        };
+        Fn1 dphi = [&](double a) {
+            vec_axpy(ctx, ws.rws, trial, x, -a, dx, N);
+            gradf(trial, gt);
+            return -vec_dot(ctx, ws.rws, gt, dx, N);
+        };
+        double beta = 0.0;
+        strong_wolfe(phi, dphi, 1.0, f_prev, dphi0, beta, f_n);      // :142
+        tr.step_lengths[step - 1] = beta;
+        vec_axpy_inplace(ctx, ws.rws, x, -beta, dx, N);              // :143
+        df_n = fabs(f_n - f_prev);                                   // :144
+        f_prev = f_n;
+        tr.f_history[step] = f_n;                                    // :146
+    }
+    if (o.steps == 0) f_n = f_prev;
+    tr.steps = o.steps;
+    tr.minimum = f_n;
+    rt_d2d(x_out, x, b, ctx->stream);
+    rt_event_record(ctx->ev1, ctx->stream);
+    rt_sync(ctx->stream);
+    ctx->newton_ms = rt_event_ms(ctx->ev0, ctx->ev1);
+    if (f_out) *f_out = f_n;
+    if (tr_out) *tr_out = tr;
+}
+
+void step_dev(mgvib200_model* m, const double* center, const double* Z1, const double* Z2, int64_t n, int dense,
+              const mgvib200_cg_opts& cg, const mgvib200_newtoncg_opts& o, double* samples, double* center_out,
+              double* mnlp, int64_t* iters_host, mgvib200_newtoncg_trace* tr, bool optimize) {
+    Engine* E = m->eng;
+    const long long N = E->n_theta;
+    E->linearize(center);                                            // ResidualSampler ctor, :133
+    m->linearized = true;
+    static thread_local DevBuf Rbuf, ReduceDummy;
+    static thread_local ReduceWs rws;
+    Rbuf.ensure(sizeof(double) * N * n);
+    double* R = Rbuf.as<double>();
+    if (dense) {
+        E->sample_dense(Z1, n, R, nullptr);                          // :134 with MatrixInversion
+        if (iters_host) for (int64_t i = 0; i < n; ++i) iters_host[i] = 0;
+    } else {
+        E->sample_cg(Z1, Z2, n, cg, R, iters_host, nullptr);         // :134
+    }
+    const double sampler_ms = m->ctx->sampler_ms;
+    const double* c_final = center;
+    if (optimize) {
+        newtoncg_dev(m, center, R, n, o, center_out, mnlp, tr);      // :135-139
+        c_final = center_out;
+    }
+    m->ctx->sampler_ms = sampler_ms;
+    vec_build_samples(m->ctx, rws, c_final, R, N, (int)n, samples);  // :140
+    rt_sync(m->ctx->stream);
+}
+
+}  // namespace
+
+// ==============================================================================================
+extern "C" {
+
+const char* mgvib200_version(void) { return "mgvib200 0.1 (sm_100a)"; }
+
+int mgvib200_init(int device_id, mgvib200_ctx** out) {
+    if (!out) return MGVIB200_ERR_INVALID;
+    *out = nullptr;
+    mgvib200_ctx* ctx = new mgvib200_ctx();
+    int rc = guarded(nullptr, [&] {
+        ctx->device = device_id;
+        rt_set_device(device_id);
+        ctx->stream = rt_stream_create();
+        ctx->ev0 = rt_event_create();
+        ctx->ev1 = rt_event_create();
+        ctx->h_pinned = (int*)rt_host_alloc(65536);
+#if defined(__CUDACC__) && !defined(MGVI_SIMT_EMU)
+        cudaDeviceProp prop;
+        RT_CUDA(cudaGetDeviceProperties(&prop, device_id));
+        ctx->sm_count = prop.multiProcessorCount;
+        if (prop.major < 10) throw RtError{"libmgvib200 is built for sm_100a (B200) only", MGVIB200_ERR_UNSUPPORTED};
+#endif
+    });
+    if (rc != MGVIB200_OK) { delete ctx; return rc; }
+    *out = ctx;
+    return MGVIB200_OK;
+}
+
+void mgvib200_destroy(mgvib200_ctx* ctx) {
+    if (!ctx) return;
+    comm_destroy(ctx);
+    rt_host_free(ctx->h_pinned);
+    rt_event_destroy(ctx->ev0);
+    rt_event_destroy(ctx->ev1);
+    rt_stream_destroy(ctx->stream);
+    delete ctx;
+}
+
+const char* mgvib200_last_error(mgvib200_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_last_global_error.c_str();
+}
+
+int mgvib200_comm_unique_id(uint8_t out_id[128]) {
+    return guarded(nullptr, [&] { comm_unique_id(out_id); });
+}
+
+int mgvib200_comm_init(mgvib200_ctx* ctx, int rank, int world_size, const uint8_t id[128]) {
+    if (!ctx) return MGVIB200_ERR_INVALID;
+    return guarded(ctx, [&] { rt_set_device(ctx->device); comm_init(ctx, rank, world_size, id); });
+}
+
+int mgvib200_model_create(mgvib200_ctx* ctx, const mgvib200_model_desc* d, mgvib200_model** out) {
+    if (!ctx || !d || !out) return MGVIB200_ERR_INVALID;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        rt_set_device(ctx->device);
+        Engine* e = nullptr;
+        switch (d->kind) {
+            case MGVIB200_MODEL_FIELD_DHT: e = make_field_engine(ctx, *d); break;
+            case MGVIB200_MODEL_POLY: e = make_poly_engine(ctx, *d); break;
+            case MGVIB200_MODEL_DENSE_LINEAR: e = make_dense_engine(ctx, *d); break;
+            default: throw RtError{"unknown model kind", MGVIB200_ERR_INVALID};
+        }
+        mgvib200_model* m = new mgvib200_model();
+        m->ctx = ctx;
+        m->eng = e;
+        *out = m;
+    });
+}
+
+void mgvib200_model_destroy(mgvib200_model* m) {
+    if (!m) return;
+    delete m->eng;
+    for (auto& s : m->stage) s.release();
+    delete m;
+}
+
+int64_t mgvib200_model_n_theta(const mgvib200_model* m) { return m ? m->eng->n_theta : -1; }
+int64_t mgvib200_model_n_lambda(const mgvib200_model* m) { return m ? m->eng->n_lambda : -1; }
+
+// ---- device-pointer entry points ---------------------------------------------------------------
+int mgvib200_linearize_dev(mgvib200_model* m, const double* center_dev) {
+    if (!m) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        rt_set_device(m->ctx->device);
+        m->eng->linearize(center_dev);
+        m->linearized = true;
+        rt_sync(m->ctx->stream);
+    });
+}
+
+int mgvib200_metric_apply_dev(mgvib200_model* m, const double* V, int64_t k, double* MV) {
+    if (!m) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        need(m->linearized, "metric_apply: call mgvib200_linearize first");
+        need(k >= 1, "metric_apply: k must be >= 1");
+        rt_set_device(m->ctx->device);
+        m->eng->metric_apply(V, k, MV);
+        rt_sync(m->ctx->stream);
+    });
+}
+
+int mgvib200_sample_residuals_cg_dev(mgvib200_model* m, const double* Z1, const double* Z2, int64_t n,
+                                     const mgvib200_cg_opts* opts, double* R, int64_t* iters_host,
+                                     double* rnorm_host) {
+    if (!m) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        need(m->linearized, "sample_residuals_cg: call mgvib200_linearize first");
+        need(n >= 1, "sample_residuals_cg: n must be >= 1");
+        rt_set_device(m->ctx->device);
+        m->eng->sample_cg(Z1, Z2, n, cg_defaults(opts), R, iters_host, rnorm_host);
+    });
+}
+
+int mgvib200_step_dev(mgvib200_model* m, const double* center, const double* Z1, const double* Z2, int64_t n,
+                      int dense, const mgvib200_cg_opts* cg, const mgvib200_newtoncg_opts* opts, double* samples,
+                      double* center_out, double* mnlp, int64_t* iters_host, mgvib200_newtoncg_trace* trace) {
+    if (!m) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        need(n >= 1, "step: n must be >= 1");
+        rt_set_device(m->ctx->device);
+        step_dev(m, center, Z1, Z2, n, dense, cg_defaults(cg), ncg_defaults(opts), samples, center_out, mnlp,
+                 iters_host, trace, true);
+    });
+}
+
+// ---- host-pointer entry points (copy in, run, copy out) ------------------------------------------
+int mgvib200_linearize(mgvib200_model* m, const double* center) {
+    if (!m || !center) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        rt_set_device(m->ctx->device);
+        double* c = stage_in(m, 0, center, m->eng->n_theta);
+        m->eng->linearize(c);
+        m->linearized = true;
+        rt_sync(m->ctx->stream);
+    });
+}
+
+int mgvib200_get_weights(mgvib200_model* m, double* w, double* q) {
+    if (!m) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        need(m->linearized, "get_weights: call mgvib200_linearize first");
+        rt_set_device(m->ctx->device);
+        m->eng->get_weights(w, q);
+    });
+}
+
+int mgvib200_metric_apply(mgvib200_model* m, const double* V, int64_t k, double* MV) {
+    if (!m || !V || !MV) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        need(m->linearized, "metric_apply: call mgvib200_linearize first");
+        need(k >= 1, "metric_apply: k must be >= 1");
+        rt_set_device(m->ctx->device);
+        const size_t cnt = (size_t)m->eng->n_theta * k;
+        double* v = stage_in(m, 1, V, cnt);
+        double* o = stage_out(m, 2, cnt);
+        m->eng->metric_apply(v, k, o);
+        rt_d2h(MV, o, sizeof(double) * cnt, m->ctx->stream);
+        rt_sync(m->ctx->stream);
+    });
+}
+
+int mgvib200_sample_residuals_cg(mgvib200_model* m, const double* Z1, const double* Z2, int64_t n,
+                                 const mgvib200_cg_opts* opts, double* R, int64_t* iters, double* final_rnorm) {
+    if (!m || !Z1 || !Z2 || !R) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        need(m->linearized, "sample_residuals_cg: call mgvib200_linearize first");
+        need(n >= 1, "sample_residuals_cg: n must be >= 1");
+        rt_set_device(m->ctx->device);
+        double* z1 = stage_in(m, 1, Z1, (size_t)m->eng->n_lambda * n);
+        double* z2 = stage_in(m, 2, Z2, (size_t)m->eng->n_theta * n);
+        double* r = stage_out(m, 3, (size_t)m->eng->n_theta * n);
+        m->eng->sample_cg(z1, z2, n, cg_defaults(opts), r, iters, final_rnorm);
+        rt_d2h(R, r, sizeof(double) * m->eng->n_theta * n, m->ctx->stream);
+        rt_sync(m->ctx->stream);
+    });
+}
+
+int mgvib200_sample_residuals_dense(mgvib200_model* m, const double* Z, int64_t n, double* R, double* L) {
+    if (!m || !Z || !R) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        need(m->linearized, "sample_residuals_dense: call mgvib200_linearize first");
+        need(n >= 1, "sample_residuals_dense: n must be >= 1");
+        rt_set_device(m->ctx->device);
+        const size_t nt = (size_t)m->eng->n_theta;
+        double* z = stage_in(m, 1, Z, nt * n);
+        double* r = stage_out(m, 3, nt * n);
+        double* l = L ? stage_out(m, 4, nt * nt) : nullptr;
+        m->eng->sample_dense(z, n, r, l);
+        rt_d2h(R, r, sizeof(double) * nt * n, m->ctx->stream);
+        if (L) rt_d2h(L, l, sizeof(double) * nt * nt, m->ctx->stream);
+        rt_sync(m->ctx->stream);
+    });
+}
+
+int mgvib200_kl_value_grad(mgvib200_model* m, const double* x, const double* R, int64_t n, double* f, double* grad) {
+    if (!m || !x || !R || !f) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        need(n >= 1, "kl_value_grad: n must be >= 1");
+        rt_set_device(m->ctx->device);
+        const size_t nt = (size_t)m->eng->n_theta;
+        double* xd = stage_in(m, 0, x, nt);
+        double* rd = stage_in(m, 3, R, nt * n);
+        double* gd = grad ? stage_out(m, 5, nt) : nullptr;
+        *f = m->eng->kl_value_grad(xd, rd, n, gd);
+        if (grad) rt_d2h(grad, gd, sizeof(double) * nt, m->ctx->stream);
+        rt_sync(m->ctx->stream);
+    });
+}
+
+int mgvib200_mean_metric_apply(mgvib200_model* m, const double* x, const double* R, int64_t n, const double* u,
+                               double* out) {
+    if (!m || !x || !R || !u || !out) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        need(n >= 1, "mean_metric_apply: n must be >= 1");
+        rt_set_device(m->ctx->device);
+        const size_t nt = (size_t)m->eng->n_theta;
+        double* xd = stage_in(m, 0, x, nt);
+        double* rd = stage_in(m, 3, R, nt * n);
+        double* ud = stage_in(m, 5, u, nt);
+        double* od = stage_out(m, 6, nt);
+        m->eng->mean_metric_prepare(xd, rd, n);
+        m->eng->mean_metric_apply(ud, od);
+        rt_d2h(out, od, sizeof(double) * nt, m->ctx->stream);
+        rt_sync(m->ctx->stream);
+    });
+}
+
+int mgvib200_newtoncg(mgvib200_model* m, const double* x0, const double* R, int64_t n,
+                      const mgvib200_newtoncg_opts* opts, double* x, double* f, mgvib200_newtoncg_trace* trace) {
+    if (!m || !x0 || !R || !x) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        need(n >= 1, "newtoncg: n must be >= 1");
+        rt_set_device(m->ctx->device);
+        const size_t nt = (size_t)m->eng->n_theta;
+        double* xd = stage_in(m, 0, x0, nt);
+        double* rd = stage_in(m, 3, R, nt * n);
+        double* od = stage_out(m, 6, nt);
+        newtoncg_dev(m, xd, rd, n, ncg_defaults(opts), od, f, trace);
+        rt_d2h(x, od, sizeof(double) * nt, m->ctx->stream);
+        rt_sync(m->ctx->stream);
+    });
+}
+
+int mgvib200_build_samples(mgvib200_model* m, const double* center, const double* R, int64_t n, double* samples) {
+    if (!m || !center || !R || !samples) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        need(n >= 1, "build_samples: n must be >= 1");
+        rt_set_device(m->ctx->device);
+        const size_t nt = (size_t)m->eng->n_theta;
+        double* cd = stage_in(m, 0, center, nt);
+        double* rd = stage_in(m, 3, R, nt * n);
+        double* sd = stage_out(m, 7, nt * 2 * n);
+        static thread_local ReduceWs rws;
+        vec_build_samples(m->ctx, rws, cd, rd, (long long)nt, (int)n, sd);
+        rt_d2h(samples, sd, sizeof(double) * nt * 2 * n, m->ctx->stream);
+        rt_sync(m->ctx->stream);
+    });
+}
+
+static int step_host(mgvib200_model* m, const double* center, const double* Z1, const double* Z2, int64_t n,
+                     int dense, const mgvib200_cg_opts* cg, const mgvib200_newtoncg_opts* opts, double* samples,
+                     double* center_out, double* mnlp, int64_t* iters, mgvib200_newtoncg_trace* trace,
+                     bool optimize) {
+    if (!m || !center || !Z1 || !samples) return MGVIB200_ERR_INVALID;
+    if (!dense && !Z2) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        need(n >= 1, "step: n must be >= 1");
+        rt_set_device(m->ctx->device);
+        const size_t nt = (size_t)m->eng->n_theta, nl = (size_t)m->eng->n_lambda;
+        double* cd = stage_in(m, 0, center, nt);
+        double* z1 = stage_in(m, 1, Z1, dense ? nt * n : nl * n);
+        double* z2 = dense ? nullptr : stage_in(m, 2, Z2, nt * n);
+        double* sd = stage_out(m, 7, nt * 2 * n);
+        double* od = stage_out(m, 6, nt);
+        step_dev(m, cd, z1, z2, n, dense, cg_defaults(cg), ncg_defaults(opts), sd, od, mnlp, iters, trace,
+                 optimize);
+        rt_d2h(samples, sd, sizeof(double) * nt * 2 * n, m->ctx->stream);
+        if (center_out && optimize) rt_d2h(center_out, od, sizeof(double) * nt, m->ctx->stream);
+        rt_sync(m->ctx->stream);
+    });
+}
+
+int mgvib200_step(mgvib200_model* m, const double* center, const double* Z1, const double* Z2, int64_t n, int dense,
+                  const mgvib200_cg_opts* cg, const mgvib200_newtoncg_opts* opts, double* samples,
+                  double* center_out, double* mnlp, int64_t* sampler_iters, mgvib200_newtoncg_trace* trace) {
+    if (!center_out || !mnlp) return MGVIB200_ERR_INVALID;
+    return step_host(m, center, Z1, Z2, n, dense, cg, opts, samples, center_out, mnlp, sampler_iters, trace, true);
+}
+
+int mgvib200_sample(mgvib200_model* m, const double* center, const double* Z1, const double* Z2, int64_t n,
+                    int dense, const mgvib200_cg_opts* cg, double* samples, int64_t* sampler_iters) {
+    return step_host(m, center, Z1, Z2, n, dense, cg, nullptr, samples, nullptr, nullptr, sampler_iters, nullptr,
+                     false);
+}
+
+// ---- raw device memory for the benchmark driver --------------------------------------------------
+void* mgvib200_dev_alloc(mgvib200_ctx* ctx, int64_t bytes) {
+    if (!ctx || bytes < 0) return nullptr;
+    void* p = nullptr;
+    guarded(ctx, [&] { rt_set_device(ctx->device); p = rt_malloc((size_t)bytes); });
+    return p;
+}
+void mgvib200_dev_free(mgvib200_ctx* ctx, void* p) {
+    if (!ctx) return;
+    guarded(ctx, [&] { rt_set_device(ctx->device); rt_free(p); });
+}
+int mgvib200_memcpy_h2d(mgvib200_ctx* ctx, void* dst, const void* src, int64_t bytes) {
+    if (!ctx) return MGVIB200_ERR_INVALID;
+    return guarded(ctx, [&] { rt_set_device(ctx->device); rt_h2d(dst, src, (size_t)bytes, ctx->stream); rt_sync(ctx->stream); });
+}
+int mgvib200_memcpy_d2h(mgvib200_ctx* ctx, void* dst, const void* src, int64_t bytes) {
+    if (!ctx) return MGVIB200_ERR_INVALID;
+    return guarded(ctx, [&] { rt_set_device(ctx->device); rt_d2h(dst, src, (size_t)bytes, ctx->stream); rt_sync(ctx->stream); });
+}
+
+int64_t mgvib200_launch_count(mgvib200_ctx* ctx, int reset) {
+    if (!ctx) return -1;
+    const int64_t v = ctx->launches;
+    if (reset) ctx->launches = 0;
+    return v;
+}
+
+int mgvib200_last_timing(mgvib200_ctx* ctx, double* sampler_ms, double* newton_ms, int64_t* lockstep_iters) {
+    if (!ctx) return MGVIB200_ERR_INVALID;
+    if (sampler_ms) *sampler_ms = ctx->sampler_ms;
+    if (newton_ms) *newton_ms = ctx->newton_ms;
+    if (lockstep_iters) *lockstep_iters = ctx->lockstep_iters;
+    return MGVIB200_OK;
+}
+
+void* mgvib200_stream(mgvib200_ctx* ctx) { return ctx ? (void*)(intptr_t)ctx->stream : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// Host-side state of libmgvib200: context, model handles and the per-kind engines.
+#pragma once
+#include <math.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/mgvi_b200.h"
+#include "rt.h"
+#include "vec_ops.h"
+
+namespace mgvi {
+
+struct Comm;   // NCCL communicator wrapper (comm.cu); null = single GPU
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    void ensure(size_t b) {
+        if (b <= bytes) return;
+        rt_free(p);
+        p = nullptr; bytes = 0;
+        p = rt_malloc(b);
+        bytes = b;
+    }
+    void release() { rt_free(p); p = nullptr; bytes = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace mgvi
+
+struct mgvib200_ctx {
+    int device = 0;
+    mgvi::rt_stream stream{};
+    std::string err;
+    int64_t launches = 0;
+    mgvi::Comm* comm = nullptr;
+    int rank = 0, world = 1;
+    mgvi::rt_event ev0{}, ev1{};
+    double sampler_ms = 0.0, newton_ms = 0.0;
+    int64_t lockstep_iters = 0;
+    int* h_pinned = nullptr;        // small pinned staging area (64 KB)
+    int sm_count = 148;
+};
+
+namespace mgvi {
+
+// reduction scratch shared by all kernels of a model
+struct ReduceWs {
+    DevBuf partials;   // doubles
+    DevBuf counters;   // unsigned, zero-initialised, self-resetting
+    DevBuf red;        // doubles: small result slots
+    size_t ncounters = 0;
+};
+
+struct CgWs {
+    int nvec = 0;
+    DevBuf gamma, alpha, beta, eps, rnorm, pAp, iters, active, n_active;
+    CgScalars scalars(double atol, double rtol, long long itmax, int flavor) const {
+        CgScalars c;
+        c.gamma = gamma.as<double>(); c.alpha = alpha.as<double>(); c.beta = beta.as<double>();
+        c.eps = eps.as<double>(); c.rnorm = rnorm.as<double>(); c.pAp = pAp.as<double>();
+        c.iters = iters.as<int>(); c.active = active.as<int>(); c.n_active = n_active.as<int>();
+        c.atol = atol; c.rtol = rtol; c.itmax = itmax; c.flavor = flavor;
+        return c;
+    }
+    void ensure(int n) {
+        if (n <= nvec) return;
+        size_t d = sizeof(double) * n, i = sizeof(int) * n;
+        gamma.ensure(d); alpha.ensure(d); beta.ensure(d); eps.ensure(d); rnorm.ensure(d); pAp.ensure(d);
+        iters.ensure(i); active.ensure(i); n_active.ensure(sizeof(int) * 4);
+        nvec = n;
+    }
+};
+
+// Interface every model family implements; all pointers are DEVICE pointers.
+struct Engine {
+    mgvib200_ctx* ctx = nullptr;
+    int64_t n_theta = 0, n_lambda = 0;
+    virtual ~Engine() {}
+    virtual void linearize(const double* center) = 0;
+    virtual void get_weights(double* w_host, double* q_host) = 0;
+    virtual void metric_apply(const double* V, int64_t k, double* MV) = 0;
+    virtual void sample_cg(const double* Z1, const double* Z2, int64_t n, const mgvib200_cg_opts& o, double* R,
+                           int64_t* iters_host, double* rnorm_host) = 0;
+    virtual void sample_dense(const double* Z, int64_t n, double* R, double* Lsigma_or_null) = 0;
+    // f = mean negative log posterior over x +- r_i ; grad may be null
+    virtual double kl_value_grad(const double* x, const double* R, int64_t n, double* grad) = 0;
+    // prepares the mean metric at x (weights over the '+' points) for subsequent apply calls
+    virtual void mean_metric_prepare(const double* x, const double* R, int64_t n) = 0;
+    virtual void mean_metric_apply(const double* u, double* out) = 0;
+    // Newton inner CG on the prepared mean metric: init with rhs g, then single updates
+    virtual void ncg_init(const double* g) = 0;
+    virtual bool ncg_active() = 0;          // iterator would yield another update
+    virtual void ncg_update() = 0;          // one CG update (dx += alpha u ...)
+    virtual const double* ncg_dx() = 0;     // current dx (device)
+};
+
+Engine* make_field_engine(mgvib200_ctx* ctx, const mgvib200_model_desc& d);
+Engine* make_poly_engine(mgvib200_ctx* ctx, const mgvib200_model_desc& d);
+Engine* make_dense_engine(mgvib200_ctx* ctx, const mgvib200_model_desc& d);
+
+// communicator (comm.cu)
+void comm_allreduce_sum(mgvib200_ctx* ctx, double* dev, long long count);
+int64_t comm_global_count(mgvib200_ctx* ctx, int64_t local);
+
+// generic vector helpers (vec_host.cu)
+void vec_launch(mgvib200_ctx* ctx, ReduceWs& ws, VecParams P);
+void reduce_ws_ensure(ReduceWs& ws, mgvib200_ctx* ctx, size_t npartials, size_t ncounters);
+double vec_dot(mgvib200_ctx* ctx, ReduceWs& ws, const double* a, const double* b, long long N);
+void vec_axpy(mgvib200_ctx* ctx, ReduceWs& ws, double* out, const double* x, double a, const double* y, long long N);
+void vec_axpy_inplace(mgvib200_ctx* ctx, ReduceWs& ws, double* x, double a, const double* y, long long N);
+void vec_build_samples(mgvib200_ctx* ctx, ReduceWs& ws, const double* c, const double* R, long long N, int n,
+                       double* samples);
+void vec_sum_chunks(mgvib200_ctx* ctx, ReduceWs& ws, const double* in, long long ld, int nsum, double scale,
+                    double* out, long long N);
+void vec_cg_init(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, const double* b, long long b_ld, double* x,
+                 double* r, double* p, long long N, int nvec);
+void vec_cg_update(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* x, double* r, const double* p,
+                   const double* Ap, long long N, int nvec);
+
+}  // namespace mgvi
+
+struct mgvib200_model {
+    mgvib200_ctx* ctx = nullptr;
+    mgvi::Engine* eng = nullptr;
+    mgvi::DevBuf stage[8];      // host-pointer API staging buffers
+    bool linearized = false;
+};

@@ -1,0 +1,599 @@
+// Correlated-field engine: s = c * H(A . xi) + offset, lambda = g(s), Normal or Poisson data.
+// Reference models: test/test_models/model_fft_gp.jl:60-72, docs/src/advanced_tutorial_lit.jl:253-307.
+// Everything here is host orchestration of the kernels in field_pass.h / vec_ops.h; all pointers
+// are device pointers.
+#include <math.h>
+#include <algorithm>
+#include "engine.h"
+#include "kernels.h"
+
+namespace mgvi {
+
+SIMT_GLOBAL(256) k_naive_axis(SIMT_KARGS(NaiveParams)) {
+    SIMT_SMEM_DECL
+    naive_axis_body(P, simt_smem);
+}
+
+namespace {
+
+const int kNaiveMaxAxis = 4096;
+const long long kFastMaxAxis = 4096;
+
+bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
+int ilog2(long long v) { int l = 0; while ((1LL << l) < v) ++l; return l; }
+
+struct PassGeo {
+    int geo, n, log2n, L, G, threads;
+    long long inner, units_per_vec, ntb;
+    size_t smem;
+};
+
+struct FieldEngine : Engine {
+    int ndim = 1;
+    long long dims[3] = {1, 1, 1};
+    long long N = 0;
+    bool fast = false;
+    double c = 1, offset = 0, sigma = 1, inv_sigma2 = 1;
+    int link = LINK_EXP, like = LIKE_POISSON, layout = 0;
+    long long z1_ld = 0, z1_stride = 1;
+    double const_term = 0.0;    // per-point constants of -loglike and of the prior
+    int max_L = 4;
+
+    DevBuf A, data, w, q, wbar, center;
+    std::map<long long, DevBuf> tw, cas;
+    ReduceWs rws;
+    CgWs cgws, ncgws;
+    DevBuf ws_r, ws_p, ws_t;          // sampler CG vectors [nvec][N]
+    DevBuf pt_t;                      // per-point scratch [npoints][N]
+    DevBuf acc;                       // chunk accumulators
+    DevBuf qsum;                      // N + 2
+    DevBuf n_x, n_r, n_p, n_t;        // Newton CG state (single vector)
+    DevBuf tmpA, tmpB;                // generic-path staging [nvec][N]
+    CgScalars ncg_sc;
+    bool ncg_first = true;
+    int h_ncg[2] = {0, 0};
+
+    ~FieldEngine() override {
+        DevBuf* all[] = {&A, &data, &w, &q, &wbar, &center, &ws_r, &ws_p, &ws_t, &pt_t, &acc, &qsum, &n_x, &n_r,
+                         &n_p, &n_t, &tmpA, &tmpB, &rws.partials, &rws.counters, &rws.red};
+        for (auto* b : all) b->release();
+        for (auto& kv : tw) kv.second.release();
+        for (auto& kv : cas) kv.second.release();
+        DevBuf* cg[] = {&cgws.gamma, &cgws.alpha, &cgws.beta, &cgws.eps, &cgws.rnorm, &cgws.pAp, &cgws.iters,
+                        &cgws.active, &cgws.n_active, &ncgws.gamma, &ncgws.alpha, &ncgws.beta, &ncgws.eps,
+                        &ncgws.rnorm, &ncgws.pAp, &ncgws.iters, &ncgws.active, &ncgws.n_active};
+        for (auto* b : cg) b->release();
+    }
+
+    // ------------------------------------------------------------------------------------------
+    void setup(const mgvib200_model_desc& d) {
+        ndim = d.ndim;
+        if (ndim < 1 || ndim > 3) throw RtError{"FIELD_DHT: ndim must be 1..3", 1};
+        N = 1;
+        for (int i = 0; i < ndim; ++i) {
+            dims[i] = d.dims[i];
+            if (dims[i] < 1) throw RtError{"FIELD_DHT: bad dims", 1};
+            N *= dims[i];
+        }
+        if (d.n_data != N) throw RtError{"FIELD_DHT: n_data must equal prod(dims)", 1};
+        if (!d.amplitude || !d.data) throw RtError{"FIELD_DHT: amplitude and data are required", 1};
+        c = d.scale; offset = d.offset; link = d.link; like = d.likelihood; sigma = d.sigma;
+        if (like == LIKE_NORMAL && !(sigma > 0)) throw RtError{"FIELD_DHT: sigma must be positive", 1};
+        inv_sigma2 = (1.0 / sigma) * (1.0 / sigma);
+        layout = (like == LIKE_POISSON) ? MGVIB200_LAYOUT_MU_ONLY : d.lambda_layout;
+        n_theta = N;
+        n_lambda = (layout == MGVIB200_LAYOUT_MU_ONLY) ? N : 2 * N;
+        z1_ld = n_lambda;
+        z1_stride = (layout == MGVIB200_LAYOUT_INTERLEAVED) ? 2 : 1;
+        fast = true;
+        for (int i = 0; i < ndim; ++i)
+            if (!is_pow2(dims[i]) || dims[i] < 8 || dims[i] > kFastMaxAxis) fast = false;
+        if (const char* e = getenv("MGVIB200_FORCE_GENERIC")) if (atoi(e)) fast = false;
+        if (const char* e = getenv("MGVIB200_STRIDED_L")) max_L = std::max(1, atoi(e));
+        if (!fast)
+            for (int i = 0; i < ndim; ++i)
+                if (dims[i] > kNaiveMaxAxis)
+                    throw RtError{"FIELD_DHT: axis length must be a power of two in [8, 4096] or <= 4096", 3};
+        A.ensure(sizeof(double) * N);
+        data.ensure(sizeof(double) * N);
+        rt_h2d(A.p, d.amplitude, sizeof(double) * N, ctx->stream);
+        rt_h2d(data.p, d.data, sizeof(double) * N, ctx->stream);
+        w.ensure(sizeof(double) * N);
+        q.ensure(sizeof(double) * N);
+        wbar.ensure(sizeof(double) * N);
+        center.ensure(sizeof(double) * N);
+        qsum.ensure(sizeof(double) * (N + 2));
+        // constants of the objective: Distributions.jl logpdf normalisers + prior (src/mgvi_impl.jl:3-7)
+        double cl = 0.0;
+        if (like == LIKE_POISSON) {
+            for (long long i = 0; i < N; ++i) cl += lgamma(d.data[i] + 1.0);
+        } else {
+            cl = (double)N * (log(sigma) + 0.5 * log(2.0 * M_PI));
+        }
+        const_term = cl + 0.5 * (double)N * log(2.0 * M_PI);
+        for (int i = 0; i < ndim; ++i) {
+            const long long n = dims[i];
+            if (fast) {
+                if (tw.count(n)) continue;
+                std::vector<double> t(2 * n);
+                for (long long k = 0; k < n; ++k) {
+                    long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+                    t[2 * k] = (double)cosl(a);
+                    t[2 * k + 1] = (double)(-sinl(a));
+                }
+                tw[n].ensure(sizeof(double) * 2 * n);
+                rt_h2d(tw[n].p, t.data(), sizeof(double) * 2 * n, ctx->stream);
+                rt_sync(ctx->stream);
+            } else {
+                if (cas.count(n)) continue;
+                std::vector<double> t((size_t)n * n);
+                for (long long k = 0; k < n; ++k)
+                    for (long long j = 0; j < n; ++j) {
+                        long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)((j * k) % n) /
+                                        (long double)n;
+                        t[(size_t)k * n + j] = (double)(cosl(a) + sinl(a));
+                    }
+                cas[n].ensure(sizeof(double) * n * n);
+                rt_h2d(cas[n].p, t.data(), sizeof(double) * n * n, ctx->stream);
+                rt_sync(ctx->stream);
+            }
+        }
+        rt_sync(ctx->stream);
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // geometry of one axis pass
+    // ------------------------------------------------------------------------------------------
+    PassGeo geo_axis(int axis, int nvec) const {
+        PassGeo g;
+        g.n = (int)dims[axis];
+        g.log2n = ilog2(g.n);
+        const int tpl = g.n / 8;
+        g.inner = 1;
+        for (int i = axis + 1; i < ndim; ++i) g.inner *= dims[i];
+        if (ndim == 1) {
+            g.geo = GEO_PAIRVEC; g.L = 1;
+            g.units_per_vec = 1;
+            const long long npairs = (nvec + 1) / 2;
+            long long G = std::max<long long>(1, 256 / tpl);
+            long long np2 = 1; while (np2 < npairs) np2 <<= 1;
+            G = std::min(G, np2);
+            G = std::max<long long>(G, (32 + tpl - 1) / tpl);
+            g.G = (int)G;
+            g.ntb = (npairs + G - 1) / G;      // blocks (with nloop = 1)
+        } else if (axis == ndim - 1) {
+            g.geo = GEO_CONTIG; g.L = 1;
+            g.units_per_vec = (N / g.n) / 2;
+            long long G = std::max<long long>(1, 256 / tpl);
+            G = std::min(G, g.units_per_vec);
+            G = std::max<long long>(G, (32 + tpl - 1) / tpl);
+            g.G = (int)G;
+            g.ntb = (g.units_per_vec + G - 1) / G;
+        } else {
+            g.geo = GEO_STRIDED;
+            long long L = std::min<long long>(max_L, g.inner / 2);
+            while (L * tpl > 1024) L >>= 1;
+            while (kSmemHeader + L * g.n * 16 > 220 * 1024) L >>= 1;
+            if (L < 1) L = 1;
+            g.L = (int)L;
+            g.units_per_vec = (N / g.n) / (2 * L);
+            const long long upt = L * tpl;
+            long long G = std::max<long long>(1, 256 / upt);
+            G = std::min(G, g.units_per_vec);
+            G = std::max<long long>(G, (32 + upt - 1) / upt);
+            g.G = (int)G;
+            g.ntb = (g.units_per_vec + G - 1) / G;
+        }
+        g.threads = g.G * g.L * tpl;
+        g.smem = (size_t)field_pass_smem_bytes(g.n, g.L, g.G);
+        return g;
+    }
+
+    template <int PRO, int EPI, bool DBL>
+    void launch_pass(FieldPassParams P, const PassGeo& g, int nvec, int nsgrp, int nloop) {
+        P.geo = g.geo; P.n = g.n; P.log2n = g.log2n; P.L = g.L; P.G = g.G;
+        P.N = N; P.inner = g.inner; P.units_per_vec = g.units_per_vec; P.ntb = g.ntb;
+        P.nvec = nvec; P.nsgrp = nsgrp; P.nloop = nloop;
+        P.tw = tw.at(g.n).as<double2>();
+        long long grid;
+        if (g.geo == GEO_PAIRVEC) {
+            const long long npairs = (nvec + 1) / 2;
+            grid = (npairs + (long long)g.G * nloop - 1) / ((long long)g.G * nloop);
+        } else {
+            grid = g.ntb * nsgrp;
+        }
+        if (P.fin != FIN_NONE) {
+            const size_t np = (P.fin == FIN_TOTAL) ? (size_t)grid : (size_t)nvec * (size_t)g.ntb;
+            reduce_ws_ensure(rws, ctx, np, (size_t)std::max(nvec, 1));
+            P.partials = rws.partials.as<double>();
+            P.counters = rws.counters.as<unsigned>();
+        }
+        if (g.threads <= 256)
+            rt_launch(k_field_pass<PRO, EPI, DBL, 256>, grid, g.threads, g.smem, ctx->stream, P);
+        else
+            rt_launch(k_field_pass<PRO, EPI, DBL, 1024>, grid, g.threads, g.smem, ctx->stream, P);
+        ctx->launches++;
+    }
+
+    // number of chunk accumulators a looping last pass will write
+    long long acc_chunks(const PassGeo& g, int nvec, int& nsgrp, int& nloop) const {
+        if (g.geo == GEO_PAIRVEC) {
+            const long long npairs = (nvec + 1) / 2;
+            // aim for a handful of blocks; every unit accumulates its own pairs
+            long long blocks = std::min<long long>(8, (npairs + g.G - 1) / g.G);
+            blocks = std::max<long long>(blocks, 1);
+            nloop = (int)((npairs + blocks * g.G - 1) / (blocks * g.G));
+            nsgrp = 1;
+            const long long grid = (npairs + (long long)g.G * nloop - 1) / ((long long)g.G * nloop);
+            return grid * g.G;
+        }
+        nsgrp = std::min(nvec, 8);
+        nloop = (nvec + nsgrp - 1) / nsgrp;
+        return nsgrp;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // generic (any length) chain pieces
+    // ------------------------------------------------------------------------------------------
+    void naive_transform_all(double*& cur, double*& other, int nvec, const double* w_after) {
+        for (int a = 0; a < ndim; ++a) {
+            NaiveParams Q;
+            Q.in = cur; Q.out = other; Q.cas = cas.at(dims[a]).as<double>();
+            Q.w = (a == ndim - 1) ? w_after : nullptr;
+            Q.N = N; Q.n = (int)dims[a]; Q.total = (long long)nvec * N;
+            Q.inner = 1;
+            for (int i = a + 1; i < ndim; ++i) Q.inner *= dims[i];
+            rt_launch(k_naive_axis, (Q.total + 255) / 256, 256, 0, ctx->stream, Q);
+            ctx->launches++;
+            std::swap(cur, other);
+        }
+    }
+
+    template <int PRO, int EPI>
+    void chain_generic(FieldPassParams P, int nvec, bool metric, int fin_pro, double* red_pro, int fin_epi,
+                       double* red_epi, bool accumulate) {
+        tmpA.ensure(sizeof(double) * N * nvec);
+        tmpB.ensure(sizeof(double) * N * nvec);
+        double* cur = tmpA.as<double>();
+        double* other = tmpB.as<double>();
+        const long long nchunk = (N + 255) / 256;
+        P.N = N; P.nvec = nvec;
+        {
+            ElemParams E;
+            E.f = P; E.tmp = cur; E.total = (long long)nvec * N; E.nloop_all = 0;
+            E.f.fin = fin_pro; E.f.red_out = red_pro;
+            const long long grid = nchunk * nvec;
+            if (fin_pro != FIN_NONE) {
+                reduce_ws_ensure(rws, ctx, (size_t)grid, (size_t)std::max(nvec, 1));
+                E.f.partials = rws.partials.as<double>(); E.f.counters = rws.counters.as<unsigned>();
+            }
+            rt_launch(k_elem_pro<PRO>, grid, 256, 512, ctx->stream, E);
+            ctx->launches++;
+        }
+        naive_transform_all(cur, other, nvec, metric ? P.w : nullptr);
+        if (metric) naive_transform_all(cur, other, nvec, nullptr);
+        {
+            ElemParams E;
+            E.f = P; E.tmp = cur; E.total = (long long)nvec * N; E.nloop_all = accumulate ? 1 : 0;
+            E.f.fin = fin_epi; E.f.red_out = red_epi;
+            const long long grid = accumulate ? nchunk : nchunk * nvec;
+            if (fin_epi != FIN_NONE) {
+                reduce_ws_ensure(rws, ctx, (size_t)grid, (size_t)std::max(nvec, 1));
+                E.f.partials = rws.partials.as<double>(); E.f.counters = rws.counters.as<unsigned>();
+            }
+            rt_launch(k_elem_epi<EPI>, grid, 256, 512, ctx->stream, E);
+            ctx->launches++;
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // chains.  `scratch` is [nvec][N].  Returns the number of chunk accumulators written
+    // (accumulate mode) or 0.
+    // ------------------------------------------------------------------------------------------
+    template <int PRO, int EPI>
+    long long chain_forward(FieldPassParams P, int nvec, double* scratch, int fin_pro, double* red_pro, int fin_epi,
+                            double* red_epi, bool accumulate) {
+        P.scale = c * pow(0.5, ndim);
+        if (!fast) {
+            if (accumulate) { acc.ensure(sizeof(double) * N); P.acc_out = acc.as<double>(); }
+            chain_generic<PRO, EPI>(P, nvec, false, fin_pro, red_pro, fin_epi, red_epi, accumulate);
+            return accumulate ? 1 : 0;
+        }
+        if (ndim == 1) {
+            PassGeo g = geo_axis(0, nvec);
+            int nsgrp = 1, nloop = 1;
+            long long chunks = 0;
+            if (accumulate) {
+                chunks = acc_chunks(g, nvec, nsgrp, nloop);
+                acc.ensure(sizeof(double) * N * chunks);
+                P.acc_out = acc.as<double>();
+            }
+            P.fin = (fin_epi != FIN_NONE) ? fin_epi : fin_pro;
+            P.red_out = (fin_epi != FIN_NONE) ? red_epi : red_pro;
+            launch_pass<PRO, EPI, false>(P, g, nvec, nsgrp, nloop);
+            return chunks;
+        }
+        // contiguous axis first
+        {
+            FieldPassParams Q = P;
+            Q.out = scratch; Q.out_ld = N; Q.fin = fin_pro; Q.red_out = red_pro;
+            launch_pass<PRO, EPI_STORE, false>(Q, geo_axis(ndim - 1, nvec), nvec, nvec, 1);
+        }
+        for (int a = ndim - 2; a >= 1; --a) {
+            FieldPassParams Q = P;
+            Q.in = scratch; Q.in_ld = N; Q.out = scratch; Q.out_ld = N; Q.fin = FIN_NONE;
+            launch_pass<PRO_LOAD, EPI_STORE, false>(Q, geo_axis(a, nvec), nvec, nvec, 1);
+        }
+        {
+            FieldPassParams Q = P;
+            Q.in = scratch; Q.in_ld = N; Q.fin = fin_epi; Q.red_out = red_epi;
+            PassGeo g = geo_axis(0, nvec);
+            int nsgrp = nvec, nloop = 1;
+            long long chunks = 0;
+            if (accumulate) {
+                chunks = acc_chunks(g, nvec, nsgrp, nloop);
+                acc.ensure(sizeof(double) * N * chunks);
+                Q.acc_out = acc.as<double>();
+            }
+            launch_pass<PRO_LOAD, EPI, false>(Q, g, nvec, nsgrp, nloop);
+            return chunks;
+        }
+    }
+
+    template <int PRO, int EPI>
+    void chain_adjoint(FieldPassParams P, int nvec, double* scratch, int fin_epi, double* red_epi) {
+        if (!fast) {
+            chain_generic<PRO, EPI>(P, nvec, false, FIN_NONE, nullptr, fin_epi, red_epi, false);
+            return;
+        }
+        if (ndim == 1) {
+            P.fin = fin_epi; P.red_out = red_epi;
+            launch_pass<PRO, EPI, false>(P, geo_axis(0, nvec), nvec, 1, 1);
+            return;
+        }
+        {
+            FieldPassParams Q = P;
+            Q.out = scratch; Q.out_ld = N; Q.fin = FIN_NONE;
+            launch_pass<PRO, EPI_STORE, false>(Q, geo_axis(0, nvec), nvec, nvec, 1);
+        }
+        for (int a = 1; a <= ndim - 2; ++a) {
+            FieldPassParams Q = P;
+            Q.in = scratch; Q.in_ld = N; Q.out = scratch; Q.out_ld = N; Q.fin = FIN_NONE;
+            launch_pass<PRO_LOAD, EPI_STORE, false>(Q, geo_axis(a, nvec), nvec, nvec, 1);
+        }
+        {
+            FieldPassParams Q = P;
+            Q.in = scratch; Q.in_ld = N; Q.fin = fin_epi; Q.red_out = red_epi;
+            launch_pass<PRO_LOAD, EPI, false>(Q, geo_axis(ndim - 1, nvec), nvec, nvec, 1);
+        }
+    }
+
+    // M v = v + c^2 A . H( w . H(A . v) ), 2d-1 passes.  P carries PRO operands, vin, out, w.
+    template <int PRO>
+    void chain_metric(FieldPassParams P, int nvec, double* scratch, int fin, double* red) {
+        P.scale = c * c * pow(0.5, 2 * ndim);
+        if (!fast) {
+            chain_generic<PRO, EPI_METRIC>(P, nvec, true, FIN_NONE, nullptr, fin, red, false);
+            return;
+        }
+        if (ndim == 1) {
+            P.fin = fin; P.red_out = red;
+            launch_pass<PRO, EPI_METRIC, true>(P, geo_axis(0, nvec), nvec, 1, 1);
+            return;
+        }
+        {
+            FieldPassParams Q = P;
+            Q.out = scratch; Q.out_ld = N; Q.fin = FIN_NONE;
+            launch_pass<PRO, EPI_STORE, false>(Q, geo_axis(ndim - 1, nvec), nvec, nvec, 1);
+        }
+        FieldPassParams S = P;
+        S.in = scratch; S.in_ld = N; S.out = scratch; S.out_ld = N; S.fin = FIN_NONE;
+        for (int a = ndim - 2; a >= 1; --a) launch_pass<PRO_LOAD, EPI_STORE, false>(S, geo_axis(a, nvec), nvec, nvec, 1);
+        launch_pass<PRO_LOAD, EPI_STORE, true>(S, geo_axis(0, nvec), nvec, nvec, 1);
+        for (int a = 1; a <= ndim - 2; ++a) launch_pass<PRO_LOAD, EPI_STORE, false>(S, geo_axis(a, nvec), nvec, nvec, 1);
+        {
+            FieldPassParams Q = P;
+            Q.in = scratch; Q.in_ld = N; Q.fin = fin; Q.red_out = red;
+            launch_pass<PRO_LOAD, EPI_METRIC, false>(Q, geo_axis(ndim - 1, nvec), nvec, nvec, 1);
+        }
+    }
+
+    FieldPassParams base_params() const {
+        FieldPassParams P;
+        memset(&P, 0, sizeof P);
+        P.N = N;
+        P.A = A.as<double>();
+        P.data = data.as<double>();
+        P.offset = offset; P.sigma = sigma; P.inv_sigma2 = inv_sigma2;
+        P.link = link; P.likelihood = like;
+        P.fin = FIN_NONE;
+        return P;
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // Engine interface
+    // ------------------------------------------------------------------------------------------
+    void linearize(const double* x) override {
+        // a4: w = F g'^2 and q = g' sqrt(F) at lambda(center)  (src/residual_samplers.jl:4-8)
+        FieldPassParams P = base_params();
+        P.x = x; P.point_mode = POINT_CENTER;
+        P.w_out = w.as<double>(); P.q_out = q.as<double>();
+        pt_t.ensure(sizeof(double) * N);
+        chain_forward<PRO_POINT, EPI_LINEARIZE>(P, 1, pt_t.as<double>(), FIN_NONE, nullptr, FIN_NONE, nullptr, false);
+        rt_d2d(center.p, x, sizeof(double) * N, ctx->stream);
+    }
+
+    void get_weights(double* w_host, double* q_host) override {
+        if (w_host) rt_d2h(w_host, w.p, sizeof(double) * N, ctx->stream);
+        if (q_host) rt_d2h(q_host, q.p, sizeof(double) * N, ctx->stream);
+        rt_sync(ctx->stream);
+    }
+
+    void metric_apply(const double* V, int64_t k, double* MV) override {
+        FieldPassParams P = base_params();
+        P.in = V; P.in_ld = N; P.vin = V; P.vin_ld = N; P.out = MV; P.out_ld = N; P.w = w.as<double>();
+        ws_t.ensure(sizeof(double) * N * k);
+        chain_metric<PRO_AMP>(P, (int)k, ws_t.as<double>(), FIN_NONE, nullptr);
+    }
+
+    void sample_cg(const double* Z1, const double* Z2, int64_t n, const mgvib200_cg_opts& o, double* R,
+                   int64_t* iters_host, double* rnorm_host) override {
+        const int nvec = (int)n;
+        const size_t vb = sizeof(double) * N * nvec;
+        ws_r.ensure(vb); ws_p.ensure(vb); ws_t.ensure(vb);
+        cgws.ensure(nvec);
+        const long long itmax = o.maxiters > 0 ? o.maxiters : N;
+        CgScalars sc = cgws.scalars(o.abstol, o.reltol, itmax, CG_KRYLOV);
+        rt_memset(cgws.n_active.p, 0, sizeof(int) * 4, ctx->stream);
+        rt_event_record(ctx->ev0, ctx->stream);
+        // b = J'(sqrt(F) . n1) + eta ; r = p = b ; x = 0 ; gamma = b.b   (src/residual_samplers.jl:75-77)
+        {
+            FieldPassParams P = base_params();
+            P.q = q.as<double>(); P.Z1 = Z1; P.Z1_ld = z1_ld; P.Z1_off = 0; P.Z1_stride = z1_stride;
+            P.Z2 = Z2; P.Z2_ld = N;
+            P.r = ws_r.as<double>(); P.p = ws_p.as<double>(); P.xout = R;
+            P.scale = c * pow(0.5, ndim);
+            P.cg = sc;
+            chain_adjoint<PRO_RHS, EPI_RHS>(P, nvec, ws_t.as<double>(), FIN_RHS, nullptr);
+        }
+        // lock-step CG over all residual samples (Krylov.jl cg!)
+        int* h = ctx->h_pinned;
+        long long it = 0;
+        int poll = 1;
+        h[0] = 1;
+        rt_d2h(h, cgws.n_active.p, sizeof(int), ctx->stream);
+        rt_sync(ctx->stream);
+        while (h[0] > 0 && it < itmax) {
+            for (int k = 0; k < poll && it < itmax; ++k, ++it) {
+                FieldPassParams P = base_params();
+                P.r = ws_r.as<double>(); P.p = ws_p.as<double>();
+                P.vin = ws_p.as<double>(); P.vin_ld = N;
+                P.out = ws_t.as<double>(); P.out_ld = N;
+                P.w = w.as<double>();
+                P.first_iter = (it == 0);
+                P.cg = sc;
+                chain_metric<PRO_CG>(P, nvec, ws_t.as<double>(), FIN_CG_PAP, nullptr);
+                vec_cg_update(ctx, rws, sc, R, ws_r.as<double>(), ws_p.as<double>(), ws_t.as<double>(), N, nvec);
+            }
+            rt_d2h(h, cgws.n_active.p, sizeof(int), ctx->stream);
+            rt_sync(ctx->stream);
+            if (poll < 8) poll *= 2;
+        }
+        rt_event_record(ctx->ev1, ctx->stream);
+        std::vector<int> hi(nvec);
+        std::vector<double> hr(nvec);
+        rt_d2h(hi.data(), cgws.iters.p, sizeof(int) * nvec, ctx->stream);
+        rt_d2h(hr.data(), cgws.rnorm.p, sizeof(double) * nvec, ctx->stream);
+        rt_sync(ctx->stream);
+        ctx->sampler_ms = rt_event_ms(ctx->ev0, ctx->ev1);
+        long long mx = 0;
+        for (int i = 0; i < nvec; ++i) {
+            if (iters_host) iters_host[i] = hi[i];
+            if (rnorm_host) rnorm_host[i] = hr[i];
+            mx = std::max<long long>(mx, hi[i]);
+        }
+        ctx->lockstep_iters = mx;
+    }
+
+    void sample_dense(const double*, int64_t, double*, double*) override {
+        throw RtError{"FIELD_DHT: the MatrixInversion sampler is only provided for POLY and DENSE_LINEAR models", 3};
+    }
+
+    double kl_value_grad(const double* x, const double* R, int64_t n, double* grad) override {
+        const int npoints = (int)(2 * n);
+        const int64_t n_glob = comm_global_count(ctx, n);
+        reduce_ws_ensure(rws, ctx, 1, 1);
+        double* red = rws.red.as<double>();
+        rt_memset(red, 0, sizeof(double) * 2, ctx->stream);
+        pt_t.ensure(sizeof(double) * N * npoints);
+        FieldPassParams P = base_params();
+        P.x = x; P.R = R; P.R_ld = N; P.point_mode = POINT_PM; P.want_grad = grad ? 1 : 0;
+        const long long chunks = chain_forward<PRO_POINT, EPI_KL>(P, npoints, pt_t.as<double>(), FIN_TOTAL, red,
+                                                                  FIN_TOTAL, red + 1, grad != nullptr);
+        double* qs = qsum.as<double>();
+        if (grad) vec_sum_chunks(ctx, rws, acc.as<double>(), N, (int)chunks, 1.0, qs, N);
+        rt_d2d(qs + N, red, sizeof(double) * 2, ctx->stream);
+        if (grad) comm_allreduce_sum(ctx, qs, N + 2);
+        else comm_allreduce_sum(ctx, qs + N, 2);
+        double hf[2];
+        rt_d2h(hf, qs + N, sizeof(double) * 2, ctx->stream);
+        rt_sync(ctx->stream);
+        if (grad) {
+            // grad = x - (1/2n) c A . H( sum_p g'(s_p) dl/dlambda(p) )
+            FieldPassParams Q = base_params();
+            Q.in = qs; Q.in_ld = N; Q.x = x; Q.out = grad;
+            Q.scale = c * pow(0.5, ndim) / (2.0 * (double)n_glob);
+            chain_adjoint<PRO_LOAD, EPI_GRAD>(Q, 1, pt_t.as<double>(), FIN_NONE, nullptr);
+        }
+        return (hf[0] + hf[1]) / (2.0 * (double)n_glob) + const_term;
+    }
+
+    void mean_metric_prepare(const double* x, const double* R, int64_t n) override {
+        const int64_t n_glob = comm_global_count(ctx, n);
+        pt_t.ensure(sizeof(double) * N * n);
+        FieldPassParams P = base_params();
+        P.x = x; P.R = R; P.R_ld = N; P.point_mode = POINT_PLUS;
+        acc.ensure(sizeof(double) * N);
+        P.acc_out = acc.as<double>();     // non-null selects accumulation; chain_forward re-points it
+        const long long chunks = chain_forward<PRO_POINT, EPI_LINEARIZE>(P, (int)n, pt_t.as<double>(), FIN_NONE,
+                                                                         nullptr, FIN_NONE, nullptr, true);
+        vec_sum_chunks(ctx, rws, acc.as<double>(), N, (int)chunks, 1.0 / (double)n_glob, wbar.as<double>(), N);
+        comm_allreduce_sum(ctx, wbar.as<double>(), N);
+    }
+
+    void mean_metric_apply(const double* u, double* out) override {
+        FieldPassParams P = base_params();
+        P.in = u; P.in_ld = N; P.vin = u; P.vin_ld = N; P.out = out; P.out_ld = N; P.w = wbar.as<double>();
+        n_t.ensure(sizeof(double) * N);
+        chain_metric<PRO_AMP>(P, 1, n_t.as<double>(), FIN_NONE, nullptr);
+    }
+
+    void ncg_init(const double* g) override {
+        const size_t b = sizeof(double) * N;
+        n_x.ensure(b); n_r.ensure(b); n_p.ensure(b); n_t.ensure(b);
+        ncgws.ensure(1);
+        // IterativeSolvers cg_iterator!(dx, A, b; initially_zero = true): reltol = sqrt(eps), abstol = 0,
+        // maxiter = size(A, 2)  (src/newtoncg.jl:120)
+        ncg_sc = ncgws.scalars(0.0, 1.4901161193847656e-08, N, CG_ITSOLVERS);
+        rt_memset(ncgws.n_active.p, 0, sizeof(int) * 4, ctx->stream);
+        vec_cg_init(ctx, rws, ncg_sc, g, N, n_x.as<double>(), n_r.as<double>(), n_p.as<double>(), N, 1);
+        ncg_first = true;
+    }
+
+    bool ncg_active() override {
+        rt_d2h(h_ncg, ncgws.active.p, sizeof(int), ctx->stream);
+        rt_sync(ctx->stream);
+        return h_ncg[0] != 0;
+    }
+
+    void ncg_update() override {
+        FieldPassParams P = base_params();
+        P.r = n_r.as<double>(); P.p = n_p.as<double>();
+        P.vin = n_p.as<double>(); P.vin_ld = N;
+        P.out = n_t.as<double>(); P.out_ld = N;
+        P.w = wbar.as<double>();
+        P.first_iter = ncg_first ? 1 : 0;
+        P.cg = ncg_sc;
+        chain_metric<PRO_CG>(P, 1, n_t.as<double>(), FIN_CG_PAP, nullptr);
+        vec_cg_update(ctx, rws, ncg_sc, n_x.as<double>(), n_r.as<double>(), n_p.as<double>(), n_t.as<double>(), N, 1);
+        ncg_first = false;
+    }
+
+    const double* ncg_dx() override { return n_x.as<double>(); }
+};
+
+}  // namespace
+
+Engine* make_field_engine(mgvib200_ctx* ctx, const mgvib200_model_desc& d) {
+    FieldEngine* e = new FieldEngine();
+    e->ctx = ctx;
+    try {
+        e->setup(d);
+    } catch (...) {
+        delete e;
+        throw;
+    }
+    return e;
+}
+
+}  // namespace mgvi

@@ -1,0 +1,569 @@
+// Fused axis-pass kernel of the correlated-field model:  load (prologue op) -> Hartley transform
+// along one axis [-> pointwise weight -> Hartley transform again] -> store (epilogue op), with an
+// optional scalar reduction finished by the last block ("last block done" pattern, deterministic
+// order).  One kernel body serves every step of the path:
+//
+//   a5  metric-vector product  M v = v + c^2 A . H( w . H(A . v) )       (src/residual_samplers.jl:72)
+//   a6  sampler right-hand side b = c A . H(q . n1) + eta                (src/residual_samplers.jl:77)
+//   a4  linearisation weights  w = F g'^2, q = g' sqrt(F)                (src/residual_samplers.jl:4-8,
+//                                                                         src/information.jl:12-18,74-78)
+//   a9  KL value terms, a10 KL gradient input                            (src/mgvi_impl.jl:3-28, newtoncg.jl:100)
+//
+// For a d-dimensional field H is separable; the two axis-0 transforms of M v sit next to each
+// other (the axis transforms commute), so they are fused into ONE pass with the weight applied
+// in shared memory/registers: 2d-1 passes over HBM instead of 2d.
+#pragma once
+#include "fft_core.h"
+
+namespace mgvi {
+
+enum { GEO_CONTIG = 0, GEO_STRIDED = 1, GEO_PAIRVEC = 2 };
+enum { PRO_LOAD = 0, PRO_AMP = 1, PRO_CG = 2, PRO_POINT = 3, PRO_RHS = 4 };
+enum { EPI_STORE = 0, EPI_METRIC = 1, EPI_LINEARIZE = 2, EPI_RHS = 3, EPI_KL = 4, EPI_GRAD = 5 };
+enum { FIN_NONE = 0, FIN_VEC_STORE = 1, FIN_TOTAL = 2, FIN_CG_PAP = 3, FIN_RHS = 4, FIN_CG_RR = 5 };
+enum { LINK_IDENTITY = 0, LINK_EXP = 1 };
+enum { LIKE_NORMAL = 0, LIKE_POISSON = 1 };
+enum { POINT_PM = 0, POINT_PLUS = 1, POINT_CENTER = 2 };
+enum { CG_KRYLOV = 0, CG_ITSOLVERS = 1 };
+
+// Per-vector conjugate-gradient scalars, all resident in device memory so that a lock-step
+// iteration over every residual sample is a fixed sequence of launches with no host round trip.
+struct CgScalars {
+    double* gamma;     // r.r  (Krylov.jl) / residual^2 (IterativeSolvers)
+    double* alpha;
+    double* beta;
+    double* eps;       // stopping threshold per vector
+    double* rnorm;     // current ||r||
+    double* pAp;
+    int* iters;
+    int* active;       // 1 while the vector still iterates
+    int* n_active;     // number of active vectors (single int)
+    double atol, rtol;
+    long long itmax;
+    int flavor;        // CG_KRYLOV (sampler) or CG_ITSOLVERS (Newton inner CG, A.2)
+};
+
+struct FieldPassParams {
+    // ---- geometry -------------------------------------------------------------------------
+    int geo, n, log2n, L, G;
+    long long N, inner, units_per_vec, ntb;
+    int nvec, nsgrp, nloop;
+    const double2* tw;
+    // ---- operands -------------------------------------------------------------------------
+    const double* in;  long long in_ld;
+    double* out;       long long out_ld;
+    const double* vin; long long vin_ld;      // EPI_METRIC: the "+ v" operand
+    const double* A;                          // amplitude (N)
+    const double* w;                          // mid weight (N), double-transform passes
+    const double* x;                          // PRO_POINT centre / EPI_GRAD prior term (N)
+    const double* R;   long long R_ld;        // residuals (N x n)
+    int point_mode;
+    const double* q;                          // g' sqrt(F) (N), PRO_RHS
+    const double* Z1;  long long Z1_ld, Z1_off, Z1_stride;
+    const double* Z2;  long long Z2_ld;
+    double* r; double* p; double* xout;       // CG vectors (leading dimension N)
+    const double* data;                       // observations (N)
+    double* w_out; double* q_out; double* lam_out;
+    double* acc_out;                          // [nchunk][N] accumulators (gradient input / mean weight)
+    double scale, offset, sigma, inv_sigma2;
+    int link, likelihood, first_iter, want_grad;
+    // ---- reduction ------------------------------------------------------------------------
+    int fin;
+    double* partials; unsigned* counters; double* red_out;
+    CgScalars cg;
+};
+
+// ------------------------------------------------------------------------------------------
+// pair helpers: (a, b) are the two real lines of a complex line.  `adj` (strided geometry) means
+// b sits right after a in memory, so both move as one 16-byte access.
+// ------------------------------------------------------------------------------------------
+SIMT_DEVICE double2 ld_pair(const double* __restrict__ base, long long ia, long long ib, bool va, bool vb,
+                            bool adj) {
+    if (adj) return *reinterpret_cast<const double2*>(base + ia);
+    return make_double2(va ? base[ia] : 0.0, vb ? base[ib] : 0.0);
+}
+SIMT_DEVICE double2 ldg_pair(const double* __restrict__ base, long long ia, long long ib, bool va, bool vb,
+                             bool adj) {
+    if (adj) return SIMT_LDG(reinterpret_cast<const double2*>(base + ia));
+    return make_double2(va ? SIMT_LDG(base + ia) : 0.0, vb ? SIMT_LDG(base + ib) : 0.0);
+}
+SIMT_DEVICE void st_pair(double* __restrict__ base, long long ia, long long ib, bool va, bool vb, bool adj,
+                         double2 v) {
+    if (adj) { *reinterpret_cast<double2*>(base + ia) = v; return; }
+    if (va) base[ia] = v.x;
+    if (vb) base[ib] = v.y;
+}
+
+// ------------------------------------------------------------------------------------------
+// pointwise model pieces (Appendix B of SURVEY.md; src/information.jl:12-18,74-78)
+// ------------------------------------------------------------------------------------------
+SIMT_DEVICE void lin_point(const FieldPassParams& P, double sig, double& w, double& q, double& lam) {
+    lam = (P.link == LINK_EXP) ? exp(sig) : sig;
+    const double gp = (P.link == LINK_EXP) ? lam : 1.0;
+    const double F = (P.likelihood == LIKE_POISSON) ? 1.0 / lam : P.inv_sigma2;
+    w = F * gp * gp;
+    q = gp * sqrt(F);
+}
+
+// variable part of -loglike at one datum, and g' * dloglike/dlambda
+SIMT_DEVICE void kl_point(const FieldPassParams& P, double sig, double d, double& nl, double& qv) {
+    const double lam = (P.link == LINK_EXP) ? exp(sig) : sig;
+    const double gp = (P.link == LINK_EXP) ? lam : 1.0;
+    if (P.likelihood == LIKE_POISSON) {
+        const double loglam = (P.link == LINK_EXP) ? sig : log(lam);
+        nl = lam - d * loglam;
+        qv = (P.link == LINK_EXP) ? (d - lam) : (d / lam - 1.0);
+    } else {
+        const double z = (d - lam) / P.sigma;
+        nl = 0.5 * z * z;
+        qv = gp * ((d - lam) * P.inv_sigma2);
+    }
+}
+
+SIMT_DEVICE void point_decode(int mode, int s, int& i, double& sign) {
+    if (mode == POINT_PM) { i = s >> 1; sign = (s & 1) ? -1.0 : 1.0; }
+    else if (mode == POINT_PLUS) { i = s; sign = 1.0; }
+    else { i = 0; sign = 0.0; }
+}
+
+template <int PRO>
+SIMT_DEVICE double2 pro_pair(const FieldPassParams& P, int sa, int sb, long long pa, long long pb, bool va,
+                             bool vb, bool adj, double& acc_a, double& acc_b) {
+    if (PRO == PRO_LOAD) {
+        return ld_pair(P.in, sa * P.in_ld + pa, sb * P.in_ld + pb, va, vb, adj);
+    } else if (PRO == PRO_AMP) {
+        double2 v = ld_pair(P.in, sa * P.in_ld + pa, sb * P.in_ld + pb, va, vb, adj);
+        double2 a = ldg_pair(P.A, pa, pb, va, vb, adj);
+        return make_double2(a.x * v.x, a.y * v.y);
+    } else if (PRO == PRO_CG) {
+        const long long ia = sa * P.N + pa, ib = sb * P.N + pb;
+        double2 pp = ld_pair(P.p, ia, ib, va, vb, adj);
+        if (!P.first_iter) {
+            double2 rr = ld_pair(P.r, ia, ib, va, vb, adj);
+            const double ba = va ? P.cg.beta[sa] : 0.0, bb = vb ? P.cg.beta[sb] : 0.0;
+            pp = make_double2(rr.x + ba * pp.x, rr.y + bb * pp.y);
+            st_pair(P.p, ia, ib, va, vb, adj, pp);
+        }
+        double2 a = ldg_pair(P.A, pa, pb, va, vb, adj);
+        return make_double2(a.x * pp.x, a.y * pp.y);
+    } else if (PRO == PRO_POINT) {
+        double2 xv = ldg_pair(P.x, pa, pb, va, vb, adj);
+        if (P.point_mode != POINT_CENTER) {
+            int i_a, i_b; double sg_a, sg_b;
+            point_decode(P.point_mode, sa, i_a, sg_a);
+            point_decode(P.point_mode, sb, i_b, sg_b);
+            double2 rv = ld_pair(P.R, i_a * P.R_ld + pa, i_b * P.R_ld + pb, va, vb, adj);
+            xv = make_double2(xv.x + sg_a * rv.x, xv.y + sg_b * rv.y);
+        }
+        if (va) acc_a += 0.5 * xv.x * xv.x;      // prior term 1/2 |p|^2 (src/mgvi_impl.jl:3-7)
+        if (vb) acc_b += 0.5 * xv.y * xv.y;
+        double2 a = ldg_pair(P.A, pa, pb, va, vb, adj);
+        return make_double2(a.x * xv.x, a.y * xv.y);
+    } else {  // PRO_RHS
+        double2 qv = ldg_pair(P.q, pa, pb, va, vb, adj);
+        const long long za = sa * P.Z1_ld + P.Z1_off + P.Z1_stride * pa;
+        const long long zb = sb * P.Z1_ld + P.Z1_off + P.Z1_stride * pb;
+        double2 z = ld_pair(P.Z1, za, zb, va, vb, adj && P.Z1_stride == 1);
+        return make_double2(qv.x * z.x, qv.y * z.y);
+    }
+}
+
+// accv: per-element accumulators across the vector loop (gradient input / mean weight)
+template <int EPI>
+SIMT_DEVICE void epi_pair(const FieldPassParams& P, int sa, int sb, long long pa, long long pb, bool va,
+                          bool vb, bool adj, double2 val, double& acc_a, double& acc_b, double2& accv) {
+    if (EPI == EPI_STORE) {
+        st_pair(P.out, sa * P.out_ld + pa, sb * P.out_ld + pb, va, vb, adj, val);
+    } else if (EPI == EPI_METRIC) {
+        double2 vi = ld_pair(P.vin, sa * P.vin_ld + pa, sb * P.vin_ld + pb, va, vb, adj);
+        double2 a = ldg_pair(P.A, pa, pb, va, vb, adj);
+        double2 o = make_double2(vi.x + P.scale * (a.x * val.x), vi.y + P.scale * (a.y * val.y));
+        st_pair(P.out, sa * P.out_ld + pa, sb * P.out_ld + pb, va, vb, adj, o);
+        if (va) acc_a += vi.x * o.x;
+        if (vb) acc_b += vi.y * o.y;
+    } else if (EPI == EPI_LINEARIZE) {
+        double wa = 0, qa = 0, la = 0, wb = 0, qb = 0, lb = 0;
+        if (va) lin_point(P, P.scale * val.x + P.offset, wa, qa, la);
+        if (vb) lin_point(P, P.scale * val.y + P.offset, wb, qb, lb);
+        if (P.acc_out) {
+            accv.x += wa; accv.y += wb;
+        } else {
+            st_pair(P.w_out, pa, pb, va, vb, adj, make_double2(wa, wb));
+            st_pair(P.q_out, pa, pb, va, vb, adj, make_double2(qa, qb));
+            if (P.lam_out) st_pair(P.lam_out, pa, pb, va, vb, adj, make_double2(la, lb));
+        }
+    } else if (EPI == EPI_RHS) {
+        double2 a = ldg_pair(P.A, pa, pb, va, vb, adj);
+        double2 e = ld_pair(P.Z2, sa * P.Z2_ld + pa, sb * P.Z2_ld + pb, va, vb, adj);
+        double2 b = make_double2(P.scale * (a.x * val.x) + e.x, P.scale * (a.y * val.y) + e.y);
+        const long long ia = sa * P.N + pa, ib = sb * P.N + pb;
+        st_pair(P.r, ia, ib, va, vb, adj, b);
+        st_pair(P.p, ia, ib, va, vb, adj, b);
+        st_pair(P.xout, ia, ib, va, vb, adj, make_double2(0.0, 0.0));
+        if (va) acc_a += b.x * b.x;
+        if (vb) acc_b += b.y * b.y;
+    } else if (EPI == EPI_KL) {
+        double2 d = ldg_pair(P.data, pa, pb, va, vb, adj);
+        double na = 0, qa = 0, nb = 0, qb = 0;
+        if (va) kl_point(P, P.scale * val.x + P.offset, d.x, na, qa);
+        if (vb) kl_point(P, P.scale * val.y + P.offset, d.y, nb, qb);
+        acc_a += na; acc_b += nb;
+        accv.x += qa; accv.y += qb;
+    } else {  // EPI_GRAD: grad = x - scale * A . val   (scale carries c / (2n) and the 1/2 factors)
+        double2 xv = ldg_pair(P.x, pa, pb, va, vb, adj);
+        double2 a = ldg_pair(P.A, pa, pb, va, vb, adj);
+        st_pair(P.out, pa, pb, va, vb, adj,
+                make_double2(xv.x - P.scale * (a.x * val.x), xv.y - P.scale * (a.y * val.y)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// reductions
+// ------------------------------------------------------------------------------------------
+// Sum `v` over segments of `seg` consecutive threads (seg a power of two dividing the block size,
+// block size a multiple of 32).  Result valid in the first thread of each segment.  `red` is
+// >= 32 doubles of shared scratch.  All threads of the block must call.
+SIMT_DEVICE double seg_reduce(double v, int seg, double* red) {
+    const int tid = SIMT_TID;
+    if (seg <= 32) {
+        for (int m = seg >> 1; m >= 1; m >>= 1) v += SIMT_SHFL_XOR_F64(v, m);
+        return v;
+    }
+    for (int m = 16; m >= 1; m >>= 1) v += SIMT_SHFL_XOR_F64(v, m);
+    SIMT_SYNC();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    SIMT_SYNC();
+    double tot = 0.0;
+    if ((tid & (seg - 1)) == 0) {
+        const int w0 = tid >> 5, nw = seg >> 5;
+        for (int i = 0; i < nw; ++i) tot += red[w0 + i];
+    }
+    return tot;
+}
+
+SIMT_DEVICE void cg_deactivate(const CgScalars& cg, int s) {
+    cg.active[s] = 0;
+    SIMT_ATOMIC_ADD_I32(cg.n_active, -1);
+}
+
+// Scalar tail of a reduction, executed by exactly one thread per vector.
+SIMT_DEVICE void finalize_vec(int fin, const CgScalars& cg, double* red_out, int s, double tot) {
+    if (fin == FIN_VEC_STORE) {
+        red_out[s] = tot;
+    } else if (fin == FIN_TOTAL) {
+        red_out[0] = tot;
+    } else if (fin == FIN_CG_PAP) {
+        cg.pAp[s] = tot;
+        cg.alpha[s] = cg.gamma[s] / tot;
+    } else if (fin == FIN_RHS) {
+        // Krylov.jl cg! start-up: gamma = b.b, eps = atol + rtol*||b||
+        const double rn = sqrt(tot);
+        cg.gamma[s] = tot;
+        cg.rnorm[s] = rn;
+        cg.iters[s] = 0;
+        cg.beta[s] = 0.0;
+        if (cg.flavor == CG_KRYLOV) {
+            const double eps = cg.atol + cg.rtol * rn;
+            cg.eps[s] = eps;
+            const int act = (tot != 0.0) && !(rn <= eps) && (cg.itmax > 0);
+            cg.active[s] = act;
+            if (act) SIMT_ATOMIC_ADD_I32(cg.n_active, 1);
+        } else {
+            // IterativeSolvers cg_iterator! start-up: tol = max(reltol*res, abstol)
+            const double tol = fmax(cg.rtol * rn, cg.atol);
+            cg.eps[s] = tol;
+            cg.gamma[s] = rn * rn;
+            const int act = !(rn <= tol) && (cg.itmax > 0);
+            cg.active[s] = act;
+            if (act) SIMT_ATOMIC_ADD_I32(cg.n_active, 1);
+        }
+    } else if (fin == FIN_CG_RR) {
+        const double rn = sqrt(tot);
+        cg.rnorm[s] = rn;
+        const int it = cg.iters[s] + 1;
+        cg.iters[s] = it;
+        if (cg.flavor == CG_KRYLOV) {
+            const bool solved = (rn <= cg.eps[s]) || (rn + 1.0 <= 1.0);
+            cg.beta[s] = tot / cg.gamma[s];
+            cg.gamma[s] = tot;
+            if (solved || it >= cg.itmax) cg_deactivate(cg, s);
+        } else {
+            const double g_new = rn * rn;
+            cg.beta[s] = g_new / cg.gamma[s];
+            cg.gamma[s] = g_new;
+            if (rn <= cg.eps[s] || it >= cg.itmax) cg_deactivate(cg, s);
+        }
+    }
+}
+
+// Cross-block part of a reduction: thread 0 of the block publishes its partial; the last block to
+// arrive sums all partials of the vector in a fixed order and runs the scalar tail.
+// slot = index of this block among the `count` blocks contributing to vector s.
+SIMT_DEVICE void block_publish_and_finalize(int fin, const CgScalars& cg, double* red_out, double* partials,
+                                            unsigned* counters, int s, long long slot, long long count,
+                                            double block_total, double* red, int* flag) {
+    const int tid = SIMT_TID;
+    if (tid == 0) {
+        partials[(long long)s * count + slot] = block_total;
+        SIMT_FENCE();
+        const unsigned c = SIMT_ATOMIC_INC_U32(&counters[s]);
+        *flag = (c == (unsigned)(count - 1));
+    }
+    SIMT_SYNC();
+    if (*flag) {
+        SIMT_FENCE();
+        double a = 0.0;
+        for (long long i = tid; i < count; i += SIMT_NTID) a += SIMT_LDCG(&partials[(long long)s * count + i]);
+        const double tot = seg_reduce(a, SIMT_NTID, red);
+        if (tid == 0) {
+            counters[s] = 0;
+            finalize_vec(fin, cg, red_out, s, tot);
+        }
+    }
+}
+
+// shared memory: [0,256) reduction scratch, [256,260) flag, FFT buffers from byte 512
+static const int kSmemHeader = 512;
+
+SIMT_HD long long field_pass_smem_bytes(int n, int L, int G) {
+    return kSmemHeader + (long long)G * L * n * 16;
+}
+
+template <int PRO, int EPI, bool DOUBLE>
+SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_raw) {
+    const int n = P.n, n8 = n >> 3, L = P.L;
+    const int tid = SIMT_TID;
+    const int upt = n8 * L;                 // threads per unit
+    const int g = tid / upt;
+    const int tu = tid - g * upt;
+    const int l = tu % L, lt = tu / L;
+    double* red = reinterpret_cast<double*>(smem_raw);
+    int* flag = reinterpret_cast<int*>(smem_raw + 256);
+    LineView lv;
+    lv.sm = reinterpret_cast<double2*>(smem_raw + kSmemHeader) + (long long)g * L * n;
+    lv.L = L;
+    lv.l = l;
+
+    const bool pairvec = (P.geo == GEO_PAIRVEC);
+    const bool adj = (P.geo == GEO_STRIDED);
+    long long bt;
+    int sgrp;
+    if (pairvec) { bt = SIMT_BID; sgrp = 0; }
+    else { bt = SIMT_BID / P.nsgrp; sgrp = (int)(SIMT_BID % P.nsgrp); }
+    const bool use_active = (P.cg.active != nullptr);
+    if (use_active && !pairvec && P.nloop == 1) {
+        if (!P.cg.active[sgrp]) return;    // uniform for the whole block
+    }
+
+    double acc_a = 0.0, acc_b = 0.0;
+    double2 accv[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) accv[m] = make_double2(0.0, 0.0);
+    long long base_a = 0, base_b = 0, stride = 1;
+    bool unit_ok = true;
+    if (!pairvec) {
+        const long long u = bt * P.G + g;
+        unit_ok = u < P.units_per_vec;
+        if (P.geo == GEO_CONTIG) {
+            base_a = 2 * u * n; base_b = base_a + n; stride = 1;
+        } else {
+            const long long tpo = P.inner / (2 * L);
+            const long long o = u / tpo, cb = u - o * tpo;
+            base_a = o * n * P.inner + cb * 2 * L + 2 * l; base_b = base_a + 1; stride = P.inner;
+        }
+    }
+    int sa = 0, sb = 0;
+    bool va = false, vb = false;
+    for (int it = 0; it < P.nloop; ++it) {
+        if (pairvec) {
+            const long long pair = (bt * P.nloop + it) * P.G + g;
+            sa = (int)(2 * pair); sb = sa + 1;
+            va = sa < P.nvec; vb = sb < P.nvec;
+        } else {
+            sa = sb = sgrp * P.nloop + it;
+            va = vb = unit_ok && sa < P.nvec;
+        }
+        if (use_active) {
+            va = va && P.cg.active[sa];
+            vb = vb && P.cg.active[sb];
+        }
+        const bool valid = va || vb;
+        double2 v[8];
+        if (valid) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const long long k = lt + m * n8;
+                v[m] = pro_pair<PRO>(P, sa, sb, base_a + k * stride, base_b + k * stride, va, vb, adj, acc_a, acc_b);
+            }
+        }
+        if (it > 0) SIMT_SYNC();   // previous iteration's combine reads vs this iteration's writes
+        fft_line_forward(v, lv, lt, n, P.log2n, P.tw, valid);
+        if (valid) dht_combine_read(v, lv, lt, n);
+        if (DOUBLE) {
+            if (valid) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const long long k = lt + m * n8;
+                    double2 wv = ldg_pair(P.w, base_a + k * stride, base_b + k * stride, va, vb, adj);
+                    v[m] = make_double2(v[m].x * wv.x, v[m].y * wv.y);
+                }
+            }
+            SIMT_SYNC();
+            fft_line_forward(v, lv, lt, n, P.log2n, P.tw, valid);
+            if (valid) dht_combine_read(v, lv, lt, n);
+        }
+        if (valid) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const long long k = lt + m * n8;
+                epi_pair<EPI>(P, sa, sb, base_a + k * stride, base_b + k * stride, va, vb, adj, v[m], acc_a, acc_b,
+                              accv[m]);
+            }
+        }
+    }
+    // ---- accumulated per-element outputs ---------------------------------------------------
+    if ((EPI == EPI_KL && P.want_grad) || (EPI == EPI_LINEARIZE && P.acc_out != nullptr)) {
+        if (pairvec) {
+            const long long chunk = bt * P.G + g;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) P.acc_out[chunk * P.N + lt + m * n8] = accv[m].x + accv[m].y;
+        } else if (unit_ok) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const long long k = lt + m * n8;
+                st_pair(P.acc_out + (long long)sgrp * P.N, base_a + k * stride, base_b + k * stride, true, true, adj,
+                        accv[m]);
+            }
+        }
+    }
+    // ---- scalar reductions -----------------------------------------------------------------
+    if (P.fin == FIN_NONE) return;
+    if (P.fin == FIN_TOTAL) {
+        const double tot = seg_reduce(acc_a + acc_b, SIMT_NTID, red);
+        block_publish_and_finalize(P.fin, P.cg, P.red_out, P.partials, P.counters, 0, SIMT_BID, SIMT_NBID, tot, red,
+                                   flag);
+    } else if (pairvec) {
+        // every vector lives entirely inside one unit (nloop == 1 for per-vector reductions)
+        const double ta = seg_reduce(acc_a, upt, red);
+        SIMT_SYNC();
+        const double tb = seg_reduce(acc_b, upt, red);
+        if (tu == 0) {
+            if (va) finalize_vec(P.fin, P.cg, P.red_out, sa, ta);
+            if (vb) finalize_vec(P.fin, P.cg, P.red_out, sb, tb);
+        }
+    } else {
+        const double tot = seg_reduce(acc_a + acc_b, SIMT_NTID, red);
+        block_publish_and_finalize(P.fin, P.cg, P.red_out, P.partials, P.counters, sgrp, bt, P.ntb, tot, red, flag);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic (any length) path for small or non-power-of-two axes: the same prologue / epilogue
+// operators as elementwise kernels around a direct O(n^2) Hartley pass per axis.  This is what
+// the reference's own 40-pixel fixture (test/test_models/model_fft_gp.jl:17) runs through.
+// ------------------------------------------------------------------------------------------
+struct ElemParams {
+    FieldPassParams f;
+    double* tmp;           // [nvec][N] staging values
+    long long total;       // nvec * N (pro) or N (epi with loop)
+    int nloop_all;         // epi: loop over all nvec vectors per element (accumulating modes)
+};
+
+template <int PRO>
+SIMT_DEVICE void elem_pro_body(const ElemParams& E, unsigned char* smem_raw) {
+    const FieldPassParams& P = E.f;
+    double* red = reinterpret_cast<double*>(smem_raw);
+    int* flag = reinterpret_cast<int*>(smem_raw + 256);
+    // block -> (chunk of pixels, vector)
+    const long long nchunk = (P.N + SIMT_NTID - 1) / SIMT_NTID;
+    const int s = (int)(SIMT_BID % P.nvec);
+    const long long chunk = SIMT_BID / P.nvec;
+    const long long pix = chunk * SIMT_NTID + SIMT_TID;
+    const bool use_active = (PRO == PRO_CG) && (P.cg.active != nullptr);
+    if (use_active && !P.cg.active[s]) return;
+    double acc_a = 0.0, acc_b = 0.0;
+    if (pix < P.N) {
+        double2 v = pro_pair<PRO>(P, s, s, pix, pix, true, false, false, acc_a, acc_b);
+        E.tmp[(long long)s * P.N + pix] = v.x;
+    }
+    if (P.fin == FIN_NONE) return;
+    const double tot = seg_reduce(acc_a, SIMT_NTID, red);
+    if (P.fin == FIN_TOTAL)
+        block_publish_and_finalize(P.fin, P.cg, P.red_out, P.partials, P.counters, 0, SIMT_BID, SIMT_NBID, tot, red,
+                                   flag);
+    else
+        block_publish_and_finalize(P.fin, P.cg, P.red_out, P.partials, P.counters, s, chunk, nchunk, tot, red, flag);
+}
+
+template <int EPI>
+SIMT_DEVICE void elem_epi_body(const ElemParams& E, unsigned char* smem_raw) {
+    const FieldPassParams& P = E.f;
+    double* red = reinterpret_cast<double*>(smem_raw);
+    int* flag = reinterpret_cast<int*>(smem_raw + 256);
+    const long long nchunk = (P.N + SIMT_NTID - 1) / SIMT_NTID;
+    double acc_a = 0.0, acc_b = 0.0;
+    double2 accv = make_double2(0.0, 0.0);
+    if (E.nloop_all) {
+        // one block per pixel chunk, loops over every vector (accumulating epilogues)
+        const long long chunk = SIMT_BID;
+        const long long pix = chunk * SIMT_NTID + SIMT_TID;
+        if (pix < P.N) {
+            for (int s = 0; s < P.nvec; ++s) {
+                double2 val = make_double2(E.tmp[(long long)s * P.N + pix], 0.0);
+                epi_pair<EPI>(P, s, s, pix, pix, true, false, false, val, acc_a, acc_b, accv);
+            }
+            if ((EPI == EPI_KL && P.want_grad) || (EPI == EPI_LINEARIZE && P.acc_out != nullptr))
+                P.acc_out[pix] = accv.x;
+        }
+        if (P.fin == FIN_NONE) return;
+        const double tot = seg_reduce(acc_a, SIMT_NTID, red);
+        block_publish_and_finalize(P.fin, P.cg, P.red_out, P.partials, P.counters, 0, SIMT_BID, SIMT_NBID, tot, red,
+                                   flag);
+        return;
+    }
+    const int s = (int)(SIMT_BID % P.nvec);
+    const long long chunk = SIMT_BID / P.nvec;
+    const long long pix = chunk * SIMT_NTID + SIMT_TID;
+    const bool use_active = (EPI == EPI_METRIC) && (P.cg.active != nullptr);
+    if (use_active && !P.cg.active[s]) return;
+    if (pix < P.N) {
+        double2 val = make_double2(E.tmp[(long long)s * P.N + pix], 0.0);
+        epi_pair<EPI>(P, s, s, pix, pix, true, false, false, val, acc_a, acc_b, accv);
+    }
+    if (P.fin == FIN_NONE) return;
+    const double tot = seg_reduce(acc_a, SIMT_NTID, red);
+    if (P.fin == FIN_TOTAL)
+        block_publish_and_finalize(P.fin, P.cg, P.red_out, P.partials, P.counters, 0, SIMT_BID, SIMT_NBID, tot, red,
+                                   flag);
+    else
+        block_publish_and_finalize(P.fin, P.cg, P.red_out, P.partials, P.counters, s, chunk, nchunk, tot, red, flag);
+}
+
+// Direct Hartley pass along one axis of [outer][n][inner], any n: out = 2 * H(in) (the factor 2
+// matches what dht_combine_read produces so both paths share scale constants), optionally
+// multiplied by a weight AFTER the transform (mid weight of the metric).
+struct NaiveParams {
+    const double* in; double* out;
+    const double* cas;     // n x n table, cas[k*n + j] = cos + sin (2 pi j k / n)
+    const double* w;       // optional pointwise weight on the output (N), or null
+    long long N, inner, total;   // total = nvec * N
+    int n;
+};
+
+SIMT_DEVICE void naive_axis_body(const NaiveParams& P, unsigned char*) {
+    const long long idx = SIMT_BID * SIMT_NTID + SIMT_TID;
+    if (idx >= P.total) return;
+    const long long s = idx / P.N, pix = idx - s * P.N;
+    const long long in_idx = pix % P.inner;
+    const long long k = (pix / P.inner) % P.n;
+    const long long o = pix / (P.inner * P.n);
+    const double* src = P.in + s * P.N + o * P.n * P.inner + in_idx;
+    const double* row = P.cas + k * P.n;
+    double a = 0.0;
+    for (int j = 0; j < P.n; ++j) a += SIMT_LDG(row + j) * src[(long long)j * P.inner];
+    a *= 2.0;
+    if (P.w) a *= SIMT_LDG(P.w + pix);
+    P.out[idx] = a;
+}
+
+}  // namespace mgvi

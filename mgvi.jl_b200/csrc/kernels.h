@@ -1,0 +1,35 @@
+// __global__ entry points (or their emulator stand-ins) for the kernel bodies.
+#pragma once
+#include "vec_ops.h"
+
+#if defined(__CUDACC__) && !defined(MGVI_SIMT_EMU)
+#define SIMT_GLOBAL(maxt) __global__ void __launch_bounds__(maxt)
+#define SIMT_KARGS(T) const T P
+#define SIMT_SMEM_DECL extern __shared__ __align__(16) unsigned char simt_smem[];
+#else
+#define SIMT_GLOBAL(maxt) static void
+#define SIMT_KARGS(T) const T &P, unsigned char *simt_smem
+#define SIMT_SMEM_DECL
+#endif
+
+namespace mgvi {
+
+template <int PRO, int EPI, bool DOUBLE, int MAXT>
+SIMT_GLOBAL(MAXT) k_field_pass(SIMT_KARGS(FieldPassParams)) {
+    SIMT_SMEM_DECL
+    field_pass_body<PRO, EPI, DOUBLE>(P, simt_smem);
+}
+
+template <int PRO>
+SIMT_GLOBAL(256) k_elem_pro(SIMT_KARGS(ElemParams)) {
+    SIMT_SMEM_DECL
+    elem_pro_body<PRO>(P, simt_smem);
+}
+
+template <int EPI>
+SIMT_GLOBAL(256) k_elem_epi(SIMT_KARGS(ElemParams)) {
+    SIMT_SMEM_DECL
+    elem_epi_body<EPI>(P, simt_smem);
+}
+
+}  // namespace mgvi

@@ -1,0 +1,109 @@
+// Thin runtime layer under the host orchestration code: device memory, copies, stream sync,
+// events and kernel launch.  The product build (nvcc) maps it onto the CUDA runtime.  The
+// -DMGVI_SIMT_EMU build (tests/simt_emu/, TEST INFRASTRUCTURE ONLY, see simt.h) maps it onto
+// malloc/memcpy and the fiber emulator so the host logic can be exercised without a GPU.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include <string>
+#include "simt.h"
+
+namespace mgvi {
+
+struct RtError {
+    std::string msg;
+    int code;
+};
+
+#if defined(__CUDACC__) && !defined(MGVI_SIMT_EMU)
+
+typedef cudaStream_t rt_stream;
+typedef cudaEvent_t rt_event;
+
+#define RT_CUDA(call)                                                                           \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            char b_[512];                                                                       \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            throw mgvi::RtError{b_, 2};                                                         \
+        }                                                                                       \
+    } while (0)
+
+inline void rt_set_device(int dev) { RT_CUDA(cudaSetDevice(dev)); }
+inline rt_stream rt_stream_create() { rt_stream s; RT_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return s; }
+inline void rt_stream_destroy(rt_stream s) { cudaStreamDestroy(s); }
+inline void* rt_malloc(size_t bytes) { void* p = nullptr; RT_CUDA(cudaMalloc(&p, bytes ? bytes : 16)); return p; }
+inline void rt_free(void* p) { if (p) cudaFree(p); }
+inline void* rt_host_alloc(size_t bytes) { void* p = nullptr; RT_CUDA(cudaMallocHost(&p, bytes ? bytes : 16)); return p; }
+inline void rt_host_free(void* p) { if (p) cudaFreeHost(p); }
+inline void rt_h2d(void* d, const void* h, size_t b, rt_stream s) { RT_CUDA(cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, s)); }
+inline void rt_d2h(void* h, const void* d, size_t b, rt_stream s) { RT_CUDA(cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, s)); }
+inline void rt_d2d(void* d, const void* s_, size_t b, rt_stream s) { RT_CUDA(cudaMemcpyAsync(d, s_, b, cudaMemcpyDeviceToDevice, s)); }
+inline void rt_memset(void* d, int v, size_t b, rt_stream s) { RT_CUDA(cudaMemsetAsync(d, v, b, s)); }
+inline void rt_sync(rt_stream s) { RT_CUDA(cudaStreamSynchronize(s)); }
+inline rt_event rt_event_create() { rt_event e; RT_CUDA(cudaEventCreate(&e)); return e; }
+inline void rt_event_destroy(rt_event e) { cudaEventDestroy(e); }
+inline void rt_event_record(rt_event e, rt_stream s) { RT_CUDA(cudaEventRecord(e, s)); }
+inline double rt_event_ms(rt_event a, rt_event b) { float ms = 0; RT_CUDA(cudaEventSynchronize(b)); RT_CUDA(cudaEventElapsedTime(&ms, a, b)); return ms; }
+
+template <typename K, typename P>
+inline void rt_launch(K kernel, long long grid, int block, size_t smem, rt_stream s, const P& params) {
+    if (grid <= 0) return;
+    if (grid > 2147483647LL) throw RtError{"grid too large", 1};
+    if (smem > 48 * 1024) {
+        static thread_local const void* last = nullptr;
+        static thread_local size_t last_smem = 0;
+        if (last != (const void*)kernel || last_smem < smem) {
+            RT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            last = (const void*)kernel;
+            last_smem = smem;
+        }
+    }
+    kernel<<<(unsigned)grid, block, smem, s>>>(params);
+    RT_CUDA(cudaGetLastError());
+}
+
+#else  // ---------------------------------- emulation --------------------------------------------
+
+typedef int rt_stream;
+typedef int rt_event;
+inline void rt_set_device(int) {}
+inline rt_stream rt_stream_create() { return 0; }
+inline void rt_stream_destroy(rt_stream) {}
+inline void* rt_malloc(size_t bytes) {
+    size_t b = bytes ? bytes : 16;
+    void* p = aligned_alloc(256, (b + 255) / 256 * 256);
+    memset(p, 0xff, b);      // NaN-poison: uninitialised reads show up in the results
+    return p;
+}
+inline void rt_free(void* p) { free(p); }
+inline void* rt_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 16); }
+inline void rt_host_free(void* p) { free(p); }
+inline void rt_h2d(void* d, const void* h, size_t b, rt_stream) { memcpy(d, h, b); }
+inline void rt_d2h(void* h, const void* d, size_t b, rt_stream) { memcpy(h, d, b); }
+inline void rt_d2d(void* d, const void* s_, size_t b, rt_stream) { memmove(d, s_, b); }
+inline void rt_memset(void* d, int v, size_t b, rt_stream) { memset(d, v, b); }
+inline void rt_sync(rt_stream) {}
+inline rt_event rt_event_create() { return 0; }
+inline void rt_event_destroy(rt_event) {}
+inline void rt_event_record(rt_event, rt_stream) {}
+inline double rt_event_ms(rt_event, rt_event) { return 0.0; }
+
+template <typename K, typename P>
+inline void rt_launch(K kernel, long long grid, int block, size_t smem, rt_stream, const P& params) {
+    if (grid <= 0) return;
+    if (block % 32 != 0) throw RtError{"emu: block size must be a multiple of 32", 1};
+    if (smem > 227 * 1024) throw RtError{"emu: shared memory request above 227 KB", 1};
+    unsigned char* sm = (unsigned char*)aligned_alloc(1024, (smem + 1023) / 1024 * 1024 + 1024);
+    memset(sm, 0xff, smem + 1024);
+    P local = params;
+    simt_emu::launch(grid, block, [&]() { kernel(local, sm); });
+    free(sm);
+}
+
+#endif
+
+}  // namespace mgvi

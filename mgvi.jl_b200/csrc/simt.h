@@ -1,0 +1,60 @@
+// SIMT portability macros.
+//
+// Kernel BODIES in this directory are written once against the tiny vocabulary below.
+//  * Under nvcc (the product build, sm_100a) every macro maps 1:1 onto the CUDA builtin.
+//  * Under g++ with -DMGVI_SIMT_EMU (tests/simt_emu/, TEST INFRASTRUCTURE ONLY) the same bodies
+//    run on a single-threaded fiber scheduler so that index arithmetic, barrier placement and
+//    reduction logic can be checked on a box without a GPU.  The emulator runtime lives under
+//    tests/ and is never compiled into, linked with or loaded by libmgvib200.so.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(MGVI_SIMT_EMU)
+
+#include <cuda_runtime.h>
+#define SIMT_DEVICE __device__ __forceinline__
+#define SIMT_HD __host__ __device__ __forceinline__
+#define SIMT_TID ((int)threadIdx.x)
+#define SIMT_NTID ((int)blockDim.x)
+#define SIMT_BID ((long long)blockIdx.x)
+#define SIMT_NBID ((long long)gridDim.x)
+#define SIMT_SYNC() __syncthreads()
+#define SIMT_FENCE() __threadfence()
+#define SIMT_SHFL_XOR_F64(v, m) __shfl_xor_sync(0xffffffffu, (v), (m))
+#define SIMT_SHFL_IDX_I32(v, l) __shfl_sync(0xffffffffu, (v), (l))
+#define SIMT_ATOMIC_INC_U32(p) atomicAdd((p), 1u)
+#define SIMT_ATOMIC_ADD_I32(p, v) atomicAdd((p), (v))
+#define SIMT_LDG(p) __ldg(p)
+#define SIMT_LDCG(p) __ldcg(p)
+#define SIMT_KERNEL(name, params_t, body_call)                                   \
+    __global__ void name(const params_t P) {                                     \
+        extern __shared__ __align__(16) unsigned char simt_smem[];               \
+        body_call;                                                               \
+    }
+
+#else  // ------------------------------- emulation ---------------------------------------------
+
+#include "simt_emu_runtime.h"   // tests/simt_emu/ (passed with -I); defines simt_emu::*
+#include <cmath>
+#define SIMT_DEVICE inline
+#define SIMT_HD inline
+#define SIMT_TID (simt_emu::tid())
+#define SIMT_NTID (simt_emu::ntid())
+#define SIMT_BID ((long long)simt_emu::bid())
+#define SIMT_NBID ((long long)simt_emu::nbid())
+#define SIMT_SYNC() simt_emu::block_barrier()
+#define SIMT_FENCE() ((void)0)
+#define SIMT_SHFL_XOR_F64(v, m) simt_emu::shfl_xor_f64((v), (m))
+#define SIMT_SHFL_IDX_I32(v, l) simt_emu::shfl_idx_i32((v), (l))
+#define SIMT_ATOMIC_INC_U32(p) simt_emu::atomic_inc_u32(p)
+#define SIMT_ATOMIC_ADD_I32(p, v) simt_emu::atomic_add_i32((p), (v))
+#define SIMT_LDG(p) (*(p))
+#define SIMT_LDCG(p) (*(p))
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+#define __restrict__
+#define SIMT_KERNEL(name, params_t, body_call)                                   \
+    static void name(const params_t& P, unsigned char* simt_smem) { body_call; }
+
+#endif

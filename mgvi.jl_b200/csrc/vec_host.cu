@@ -1,0 +1,99 @@
+// Launch wrappers for the streaming vector kernels (vec_ops.h).
+#include "engine.h"
+#include "kernels.h"
+
+namespace mgvi {
+
+SIMT_GLOBAL(256) k_vec(SIMT_KARGS(VecParams)) {
+    SIMT_SMEM_DECL
+    vec_body(P, simt_smem);
+}
+
+static const int kVecThreads = 256;
+static const long long kVecPerBlock = 4096;
+
+void reduce_ws_ensure(ReduceWs& ws, mgvib200_ctx* ctx, size_t npartials, size_t ncounters) {
+    ws.partials.ensure(sizeof(double) * npartials);
+    ws.red.ensure(sizeof(double) * 64);
+    if (ncounters > ws.ncounters) {
+        ws.counters.release();
+        ws.counters.ensure(sizeof(unsigned) * ncounters);
+        rt_memset(ws.counters.p, 0, sizeof(unsigned) * ncounters, ctx->stream);
+        ws.ncounters = ncounters;
+    }
+}
+
+void vec_launch(mgvib200_ctx* ctx, ReduceWs& ws, VecParams P) {
+    P.per_block = kVecPerBlock;
+    P.nchunk = (P.N + kVecPerBlock - 1) / kVecPerBlock;
+    const long long grid = P.nchunk * P.nvec;
+    if (P.fin != FIN_NONE) {
+        reduce_ws_ensure(ws, ctx, (size_t)grid, (size_t)(P.nvec > 1 ? P.nvec : 1));
+        P.partials = ws.partials.as<double>();
+        P.counters = ws.counters.as<unsigned>();
+        if (!P.red_out) P.red_out = ws.red.as<double>();
+    }
+    rt_launch(k_vec, grid, kVecThreads, 512, ctx->stream, P);
+    ctx->launches++;
+}
+
+static VecParams vp_zero() {
+    VecParams P;
+    memset(&P, 0, sizeof P);
+    P.nvec = 1;
+    return P;
+}
+
+double vec_dot(mgvib200_ctx* ctx, ReduceWs& ws, const double* a, const double* b, long long N) {
+    VecParams P = vp_zero();
+    P.op = VOP_DOT; P.N = N; P.in = a; P.y = b; P.fin = FIN_TOTAL;
+    vec_launch(ctx, ws, P);
+    double h = 0.0;
+    rt_d2h(&h, ws.red.p, sizeof(double), ctx->stream);
+    rt_sync(ctx->stream);
+    return h;
+}
+
+void vec_axpy(mgvib200_ctx* ctx, ReduceWs& ws, double* out, const double* x, double a, const double* y, long long N) {
+    VecParams P = vp_zero();
+    P.op = VOP_AXPY; P.N = N; P.in = x; P.y = y; P.a = a; P.out = out;
+    vec_launch(ctx, ws, P);
+}
+
+void vec_axpy_inplace(mgvib200_ctx* ctx, ReduceWs& ws, double* x, double a, const double* y, long long N) {
+    VecParams P = vp_zero();
+    P.op = VOP_AXPY_INPLACE; P.N = N; P.out = x; P.y = y; P.a = a;
+    vec_launch(ctx, ws, P);
+}
+
+void vec_build_samples(mgvib200_ctx* ctx, ReduceWs& ws, const double* c, const double* R, long long N, int n,
+                       double* samples) {
+    VecParams P = vp_zero();
+    P.op = VOP_BUILD; P.N = N; P.nvec = n; P.in = c; P.y = R; P.out = samples;
+    vec_launch(ctx, ws, P);
+}
+
+void vec_sum_chunks(mgvib200_ctx* ctx, ReduceWs& ws, const double* in, long long ld, int nsum, double scale,
+                    double* out, long long N) {
+    VecParams P = vp_zero();
+    P.op = VOP_SUM_CHUNKS; P.N = N; P.in = in; P.in_ld = ld; P.nsum = nsum; P.scale = scale; P.out = out;
+    vec_launch(ctx, ws, P);
+}
+
+void vec_cg_init(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, const double* b, long long b_ld, double* x,
+                 double* r, double* p, long long N, int nvec) {
+    VecParams P = vp_zero();
+    P.op = VOP_CG_INIT; P.N = N; P.nvec = nvec; P.in = b; P.in_ld = b_ld; P.x = x; P.r = r; P.p = p;
+    P.fin = FIN_RHS; P.cg = cg;
+    vec_launch(ctx, ws, P);
+}
+
+void vec_cg_update(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* x, double* r, const double* p,
+                   const double* Ap, long long N, int nvec) {
+    VecParams P = vp_zero();
+    P.op = VOP_CG_UPDATE; P.N = N; P.nvec = nvec; P.x = x; P.r = r; P.p = p; P.Ap = Ap;
+    P.fin = FIN_CG_RR; P.cg = cg;
+    vec_launch(ctx, ws, P);
+}
+
+}  // namespace mgvi

@@ -1,0 +1,89 @@
+// Streaming vector kernels of the batched conjugate-gradient solve and of the Newton step
+// (fused axpy pairs with the dot product of the same pass; src/residual_samplers.jl:79-81 via
+// Krylov.jl cg!, src/newtoncg.jl:120 via IterativeSolvers cg_iterator!), plus sample assembly
+// (src/mgvi_impl.jl:152-156).
+#pragma once
+#include "field_pass.h"
+
+namespace mgvi {
+
+enum {
+    VOP_CG_UPDATE = 0,   // x += alpha p ; r -= alpha Ap ; acc = r.r          (per vector)
+    VOP_CG_INIT = 1,     // r = b ; p = b ; x = 0 ; acc = b.b                 (per vector)
+    VOP_SUM_CHUNKS = 2,  // out = scale * sum_c in[c]                          (nvec = 1)
+    VOP_AXPY = 3,        // out = x + a * y                                    (nvec = 1)
+    VOP_DOT = 4,         // acc = x . y                                        (nvec = 1)
+    VOP_BUILD = 5,       // samples[:, 2i] = c + r_i ; samples[:, 2i+1] = c - r_i   (vector = i)
+    VOP_AXPY_INPLACE = 6 // x += a * y                                         (nvec = 1)
+};
+
+struct VecParams {
+    int op, nvec, fin;
+    long long N, nchunk, per_block;
+    double* x; double* r; const double* p; const double* Ap;   // CG vectors, ld = N
+    const double* in; double* out; long long in_ld;
+    const double* y;
+    int nsum;
+    double a, scale;
+    double* partials; unsigned* counters; double* red_out;
+    CgScalars cg;
+};
+
+SIMT_DEVICE void vec_elem(const VecParams& P, int s, long long i, double alpha, double& acc) {
+    const long long gi = (long long)s * P.N + i;
+    switch (P.op) {
+        case VOP_CG_UPDATE: {
+            const double pv = P.p[gi], av = P.Ap[gi];
+            P.x[gi] += alpha * pv;
+            const double rv = P.r[gi] - alpha * av;
+            P.r[gi] = rv;
+            acc += rv * rv;
+        } break;
+        case VOP_CG_INIT: {
+            const double b = P.in[(long long)s * P.in_ld + i];
+            P.r[gi] = b;
+            const_cast<double*>(P.p)[gi] = b;
+            P.x[gi] = 0.0;
+            acc += b * b;
+        } break;
+        case VOP_SUM_CHUNKS: {
+            double t = 0.0;
+            for (int c = 0; c < P.nsum; ++c) t += P.in[(long long)c * P.in_ld + i];
+            P.out[i] = P.scale * t;
+        } break;
+        case VOP_AXPY: P.out[i] = P.in[i] + P.a * P.y[i]; break;
+        case VOP_AXPY_INPLACE: P.out[i] += P.a * P.y[i]; break;
+        case VOP_DOT: acc += P.in[i] * P.y[i]; break;
+        case VOP_BUILD: {
+            const double c = P.in[i], rv = P.y[gi];
+            P.out[(long long)(2 * s) * P.N + i] = c + rv;
+            P.out[(long long)(2 * s + 1) * P.N + i] = c - rv;
+        } break;
+    }
+}
+
+// block -> (chunk, vector); a block covers `per_block` consecutive elements of one vector.
+SIMT_DEVICE void vec_body(const VecParams& P, unsigned char* smem_raw) {
+    double* red = reinterpret_cast<double*>(smem_raw);
+    int* flag = reinterpret_cast<int*>(smem_raw + 256);
+    const int s = (int)(SIMT_BID % P.nvec);
+    const long long chunk = SIMT_BID / P.nvec;
+    const bool cg_op = (P.op == VOP_CG_UPDATE);
+    if (cg_op && !P.cg.active[s]) return;
+    const double alpha = cg_op ? P.cg.alpha[s] : 0.0;
+    const long long lo = chunk * P.per_block;
+    long long hi = lo + P.per_block;
+    if (hi > P.N) hi = P.N;
+    double acc = 0.0;
+    for (long long i = lo + SIMT_TID; i < hi; i += SIMT_NTID) vec_elem(P, s, i, alpha, acc);
+    if (P.fin == FIN_NONE) return;
+    const double tot = seg_reduce(acc, SIMT_NTID, red);
+    if (P.fin == FIN_TOTAL)
+        block_publish_and_finalize(P.fin, P.cg, P.red_out, P.partials, P.counters, 0, SIMT_BID, SIMT_NBID, tot, red,
+                                   flag);
+    else
+        block_publish_and_finalize(P.fin, P.cg, P.red_out, P.partials, P.counters, s, chunk, P.nchunk, tot, red,
+                                   flag);
+}
+
+}  // namespace mgvi
