@@ -472,6 +472,7 @@ struct FieldEngine : Engine {
                 P.w = w.as<double>();
                 P.first_iter = (it == 0);
                 P.cg = sc;
+                P.mask_active = 1;
                 chain_metric<PRO_CG>(P, nvec, ws_t.as<double>(), FIN_CG_PAP, nullptr);
                 vec_cg_update(ctx, rws, sc, R, ws_r.as<double>(), ws_p.as<double>(), ws_t.as<double>(), N, nvec);
             }
@@ -574,6 +575,7 @@ struct FieldEngine : Engine {
         P.w = wbar.as<double>();
         P.first_iter = ncg_first ? 1 : 0;
         P.cg = ncg_sc;
+        P.mask_active = 1;
         chain_metric<PRO_CG>(P, 1, n_t.as<double>(), FIN_CG_PAP, nullptr);
         vec_cg_update(ctx, rws, ncg_sc, n_x.as<double>(), n_r.as<double>(), n_p.as<double>(), n_t.as<double>(), N, 1);
         ncg_first = false;

@@ -67,6 +67,7 @@ struct FieldPassParams {
     double* acc_out;                          // [nchunk][N] accumulators (gradient input / mean weight)
     double scale, offset, sigma, inv_sigma2;
     int link, likelihood, first_iter, want_grad;
+    int mask_active;                          // skip vectors whose cg.active flag is 0 (CG iterations only)
     // ---- reduction ------------------------------------------------------------------------
     int fin;
     double* partials; unsigned* counters; double* red_out;
@@ -350,7 +351,7 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
     int sgrp;
     if (pairvec) { bt = SIMT_BID; sgrp = 0; }
     else { bt = SIMT_BID / P.nsgrp; sgrp = (int)(SIMT_BID % P.nsgrp); }
-    const bool use_active = (P.cg.active != nullptr);
+    const bool use_active = (P.mask_active != 0);
     if (use_active && !pairvec && P.nloop == 1) {
         if (!P.cg.active[sgrp]) return;    // uniform for the whole block
     }
@@ -479,7 +480,7 @@ SIMT_DEVICE void elem_pro_body(const ElemParams& E, unsigned char* smem_raw) {
     const int s = (int)(SIMT_BID % P.nvec);
     const long long chunk = SIMT_BID / P.nvec;
     const long long pix = chunk * SIMT_NTID + SIMT_TID;
-    const bool use_active = (PRO == PRO_CG) && (P.cg.active != nullptr);
+    const bool use_active = (P.mask_active != 0);
     if (use_active && !P.cg.active[s]) return;
     double acc_a = 0.0, acc_b = 0.0;
     if (pix < P.N) {
@@ -524,7 +525,7 @@ SIMT_DEVICE void elem_epi_body(const ElemParams& E, unsigned char* smem_raw) {
     const int s = (int)(SIMT_BID % P.nvec);
     const long long chunk = SIMT_BID / P.nvec;
     const long long pix = chunk * SIMT_NTID + SIMT_TID;
-    const bool use_active = (EPI == EPI_METRIC) && (P.cg.active != nullptr);
+    const bool use_active = (P.mask_active != 0);
     if (use_active && !P.cg.active[s]) return;
     if (pix < P.N) {
         double2 val = make_double2(E.tmp[(long long)s * P.N + pix], 0.0);

@@ -1,0 +1,41 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    import __graft_entry__ as g
+    return g.load_package()
+
+
+@pytest.fixture(scope="session")
+def emu_ctx(pkg):
+    """Context on the g++/fiber-emulator build of the same sources (TEST INFRASTRUCTURE; the
+    product never loads this library)."""
+    import __graft_entry__ as g
+    path = g.build_emu()
+    lib = pkg.Library(path)
+    ctx = pkg.MGVIContext(library=lib)
+    yield ctx
+    ctx.close()
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx(pkg):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    ctx = pkg.MGVIContext(device=0)      # product library; raises if libmgvib200.so is missing
+    yield ctx
+    ctx.close()

@@ -1,0 +1,113 @@
+"""CPU checks of the REAL kernel and host sources: the .cu files compiled with g++ against the
+fiber SIMT emulator (tests/simt_emu/, test infrastructure) and driven through the same C ABI,
+compared with the oracle.  Sizes are tiny (the emulator runs one thread at a time); the GPU
+tests (test_gpu_parity.py) repeat this on the product library at real sizes."""
+import numpy as np
+import pytest
+
+import oracle as O
+from golden_io import load_golden
+from helpers import RTOL, TIGHT, assert_field_ops, check_field_ops, oracle_model, rel
+
+
+def _field(pkg, dims, like, n, layout=None, std=0.5):
+    syn = pkg.synthetic
+    return syn.field_config(dims, getattr(syn, like), n, field_std=std, layout=layout)
+
+
+# every leading-radix case of the FFT (log2 n mod 3 = 0, 1, 2), single pass 1-D geometry
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 128, 256, 512])
+def test_metric_1d_all_radix_leads(pkg, emu_ctx, n):
+    cfg = _field(pkg, (n,), "LIKE_POISSON", 3)
+    m = pkg.model_from_config(cfg, emu_ctx)
+    om = oracle_model(cfg)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(**TIGHT), emu_ctx)
+    lin = om.linearize(cfg["center"])
+    V = np.random.default_rng(5).standard_normal((n, 3))       # odd count: one half-empty pair
+    MV = s.metric_apply(V)
+    MVo = np.stack([O.metric_apply(lin, V[:, i]) for i in range(3)], axis=1)
+    assert rel(MV, MVo) < RTOL
+    w, q = s.weights()
+    lam = om.rate(cfg["center"])
+    assert rel(w, lam) < RTOL and rel(q, np.sqrt(lam)) < RTOL     # Poisson + exp: w = lambda, q = sqrt(lambda)
+    m.close()
+
+
+@pytest.mark.parametrize("dims,like,layout", [
+    ((64,), "LIKE_POISSON", None),
+    ((16, 32), "LIKE_NORMAL", 2),       # interleaved [mu, sigma] layout
+    ((8, 64), "LIKE_POISSON", None),
+    ((32, 8), "LIKE_NORMAL", 1),        # blocked [mu; var] layout
+    ((8, 16, 8), "LIKE_POISSON", None),
+    ((40,), "LIKE_NORMAL", 2),          # the reference fixture's length: generic (non power of two) path
+    ((6, 10), "LIKE_POISSON", None),
+])
+def test_field_ops_vs_oracle(pkg, emu_ctx, dims, like, layout):
+    cfg = _field(pkg, dims, like, 3 if len(dims) == 1 else 2, layout)
+    assert_field_ops(check_field_ops(pkg, emu_ctx, cfg, check_step=True))
+
+
+def test_identity_link_and_normal(pkg, emu_ctx):
+    syn = pkg.synthetic
+    cfg = syn.field_config((32,), syn.LIKE_NORMAL, 2, field_std=0.5)
+    cfg["link"] = syn.LINK_IDENTITY
+    # linear-Gaussian: Newton converges in step 1, later steps divide rounding noise by rounding
+    # noise -> judged against the oracle's own reproducibility (helpers.assert_step_parity)
+    assert_field_ops(check_field_ops(pkg, emu_ctx, cfg, check_step=True), cfg)
+
+
+@pytest.mark.parametrize("name", ["fft_gp_40", "field_1d_64_poisson", "field_2d_16x32_normal",
+                                  "field_3d_8x8x16_poisson"])
+def test_golden_vectors(pkg, emu_ctx, name):
+    cfg, gold = load_golden(name)
+    m = pkg.model_from_config(cfg, emu_ctx)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(**TIGHT), emu_ctx)
+    assert rel(s.metric_apply(gold["V"]), gold["MV"]) < RTOL
+    R = pkg.sample_residuals(s, cfg["n_residuals"], draws=(cfg["Z1"], cfg["Z2"]))
+    assert rel(R, gold["R"]) < RTOL
+    f, g = pkg.kl_value_grad(m, cfg["center"], gold["R"])
+    assert abs(f - gold["f"]) / abs(gold["f"]) < RTOL and rel(g, gold["grad"]) < RTOL
+    res, c = pkg.mgvi_step(m, cfg["data"], cfg["n_residuals"], cfg["center"],
+                           pkg.MGVIConfig(linsolver=pkg.B200CG(**TIGHT)), emu_ctx, draws=(cfg["Z1"], cfg["Z2"]))
+    tr = res.info["optimizer_output"]
+    trace_equal = (tr["cg_updates"] == gold["tr_cg_updates"].tolist() and tr["f_calls"] == int(gold["tr_f_calls"]))
+    from helpers import assert_step_parity
+    assert_step_parity(cfg, rel(c, gold["step_center"]), rel(res.samples, gold["step_samples"]), trace_equal)
+    # residuals (antithetic half-differences) do not pass through the optimiser: always tight
+    assert rel(res.samples[:, 0::2] - res.samples[:, 1::2],
+               gold["step_samples"][:, 0::2] - gold["step_samples"][:, 1::2]) < RTOL
+    m.close()
+
+
+def test_cg_maxiters_and_default_tolerance(pkg, emu_ctx):
+    cfg = _field(pkg, (64,), "LIKE_POISSON", 2)
+    m = pkg.model_from_config(cfg, emu_ctx)
+    om = oracle_model(cfg)
+    # itmax reached: identical truncated iterates
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(abstol=0.0, reltol=1e-30, maxiters=7), emu_ctx)
+    R, info = pkg.sample_residuals(s, 2, draws=(cfg["Z1"], cfg["Z2"]), return_info=True)
+    Ro, ito, _ = O.sample_residuals_cg(om, cfg["center"], cfg["Z1"], cfg["Z2"], atol=0.0, rtol=1e-30, itmax=7)
+    assert info["iters"].tolist() == [7, 7] == ito.tolist()
+    assert rel(R, Ro) < RTOL
+    # reference default stopping rule (sqrt(eps) abs + rel): same iteration counts
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(), emu_ctx)
+    R, info = pkg.sample_residuals(s, 2, draws=(cfg["Z1"], cfg["Z2"]), return_info=True)
+    Ro, ito, rno = O.sample_residuals_cg(om, cfg["center"], cfg["Z1"], cfg["Z2"])
+    assert info["iters"].tolist() == ito.tolist()
+    assert rel(R, Ro) < 1e-6
+    np.testing.assert_allclose(info["final_rnorm"], rno, rtol=1e-3)
+    m.close()
+
+
+def test_single_residual_and_rng_draws(pkg, emu_ctx):
+    cfg = _field(pkg, (16, 8), "LIKE_POISSON", 1)
+    m = pkg.model_from_config(cfg, emu_ctx)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(**TIGHT), emu_ctx)
+    r1 = pkg.sample_residuals(s)                 # n omitted -> one vector (src/residual_samplers.jl:66-83)
+    assert r1.shape == (m.n_theta,)
+    emu_ctx.rng = np.random.default_rng(9)
+    a = pkg.sample_residuals(s, 2)
+    emu_ctx.rng = np.random.default_rng(9)
+    b = pkg.sample_residuals(s, 2)
+    np.testing.assert_array_equal(a, b)
+    m.close()
