@@ -200,6 +200,11 @@ int64_t mgvib200_launch_count(mgvib200_ctx* ctx, int reset);
 /* device time (ms) of the most recent sampler CG loop / Newton phase, measured with CUDA events on
  * the library's own stream, and the lock-step iteration count of the most recent sampler call */
 int mgvib200_last_timing(mgvib200_ctx* ctx, double* sampler_ms, double* newton_ms, int64_t* lockstep_iters);
+/* per-kernel device timing: CUDA events around every launch between begin and end.  `end`
+ * fills up to max_tags entries (tag, total ms, launch count) and returns how many; -1 on error.
+ * tags: field pass = 100*prologue + 10*epilogue + fused_double ; vector kernels = 1000 + op. */
+int mgvib200_profile_begin(mgvib200_ctx* ctx);
+int mgvib200_profile_end(mgvib200_ctx* ctx, int max_tags, int32_t* tags, double* ms, int64_t* counts);
 /* the CUDA stream the library launches on (cudaStream_t as void*) */
 void* mgvib200_stream(mgvib200_ctx* ctx);
 

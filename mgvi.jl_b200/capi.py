@@ -97,6 +97,8 @@ EXPORTS = {
                                     c_int64_p, C.POINTER(NewtonCGTrace)]),
     "mgvib200_launch_count": (C.c_int64, [C.c_void_p, C.c_int]),
     "mgvib200_last_timing": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_int64_p]),
+    "mgvib200_profile_begin": (C.c_int, [C.c_void_p]),
+    "mgvib200_profile_end": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), c_double_p, c_int64_p]),
     "mgvib200_stream": (C.c_void_p, [C.c_void_p]),
 }
 
@@ -129,7 +131,8 @@ _default_lib: Library | None = None
 def default_library() -> Library:
     global _default_lib
     if _default_lib is None:
-        _default_lib = Library()
+        # MGVIB200_LIB selects another build of the SAME CUDA sources (tuning experiments)
+        _default_lib = Library(os.environ.get("MGVIB200_LIB") or None)
     return _default_lib
 
 

@@ -576,6 +576,37 @@ int mgvib200_last_timing(mgvib200_ctx* ctx, double* sampler_ms, double* newton_m
     return MGVIB200_OK;
 }
 
+int mgvib200_profile_begin(mgvib200_ctx* ctx) {
+    if (!ctx) return MGVIB200_ERR_INVALID;
+    ctx->prof.clear();
+    ctx->ev_used = 0;
+    ctx->profile = true;
+    return MGVIB200_OK;
+}
+
+int mgvib200_profile_end(mgvib200_ctx* ctx, int max_tags, int32_t* tags, double* ms, int64_t* counts) {
+    if (!ctx) return -1;
+    ctx->profile = false;
+    int ntags = 0;
+    int rc = guarded(ctx, [&] {
+        rt_sync(ctx->stream);
+        std::map<int, std::pair<double, int64_t>> acc;
+        for (auto& r : ctx->prof) {
+            auto& e = acc[r.tag];
+            e.first += rt_event_ms(r.a, r.b);
+            e.second += 1;
+        }
+        for (auto& kv : acc) {
+            if (ntags >= max_tags) break;
+            tags[ntags] = kv.first; ms[ntags] = kv.second.first; counts[ntags] = kv.second.second;
+            ++ntags;
+        }
+        ctx->prof.clear();
+        ctx->ev_used = 0;
+    });
+    return rc == MGVIB200_OK ? ntags : -1;
+}
+
 void* mgvib200_stream(mgvib200_ctx* ctx) { return ctx ? (void*)(intptr_t)ctx->stream : nullptr; }
 
 }  // extern "C"

@@ -40,6 +40,26 @@ struct mgvib200_ctx {
     int64_t lockstep_iters = 0;
     int* h_pinned = nullptr;        // small pinned staging area (64 KB)
     int sm_count = 148;
+    // per-kernel timing (bench.py roofline): CUDA events around every launch while enabled
+    bool profile = false;
+    struct ProfRec { int tag; mgvi::rt_event a, b; };
+    std::vector<ProfRec> prof;
+    std::vector<mgvi::rt_event> ev_pool;
+    size_t ev_used = 0;
+    mgvi::rt_event prof_event() {
+        if (ev_used == ev_pool.size()) ev_pool.push_back(mgvi::rt_event_create());
+        return ev_pool[ev_used++];
+    }
+    void prof_pre(int tag) {
+        if (!profile) return;
+        ProfRec r; r.tag = tag; r.a = prof_event(); r.b = prof_event();
+        mgvi::rt_event_record(r.a, stream);
+        prof.push_back(r);
+    }
+    void prof_post() {
+        if (!profile) return;
+        mgvi::rt_event_record(prof.back().b, stream);
+    }
 };
 
 namespace mgvi {

@@ -11,9 +11,13 @@
 // radix-4 or radix-2 stage when log2 n is not a multiple of 3) exchange through ONE shared
 // buffer per line: write scattered, barrier, read back in the k = lt + m*n/8 arrangement,
 // barrier.  Shared memory holds double2 (16 B) chunks at index (k*L + l) for line l of L
-// side-by-side lines, XOR-swizzled on the chunk index (bits 0..2 ^= bits 3..5) -- the same
-// pattern as the TMA 128-byte swizzle -- which keeps every stage's scattered writes and linear
-// reads free of bank conflicts.
+// side-by-side lines (L a power of two), XOR-swizzled on the chunk index (bits 0..2 ^= bits
+// 3..5) -- the same pattern as the TMA 128-byte swizzle -- which keeps every stage's scattered
+// writes and linear reads free of bank conflicts.
+//
+// Everything is written for a small register footprint (the kernels want 3-4 resident blocks
+// of 256 threads per SM): power-of-two index arithmetic is shifts and masks, twiddles are
+// consumed one at a time, butterflies work in place.
 #pragma once
 #include "simt.h"
 
@@ -29,107 +33,140 @@ SIMT_HD double2 cmul_mi(double2 a) { return make_double2(a.y, -a.x); }
 
 SIMT_HD int swz(int chunk) { return chunk ^ ((chunk >> 3) & 7); }
 
+// in-place radix-2 butterfly
+SIMT_HD void bfly2(double2& a, double2& b) {
+    const double2 t = csub(a, b);
+    a = cadd(a, b);
+    b = t;
+}
+
 // 4-point forward DFT in place (natural order out).
 SIMT_HD void dft4(double2& c0, double2& c1, double2& c2, double2& c3) {
-    double2 d0 = cadd(c0, c2), d1 = csub(c0, c2), d2 = cadd(c1, c3), d3 = cmul_mi(csub(c1, c3));
-    c0 = cadd(d0, d2);
-    c1 = cadd(d1, d3);
-    c2 = csub(d0, d2);
-    c3 = csub(d1, d3);
+    bfly2(c0, c2);              // c0 = d0, c2 = d1
+    bfly2(c1, c3);              // c1 = d2, c3 = c1 - c3
+    c3 = cmul_mi(c3);           // d3
+    bfly2(c0, c1);              // c0 = Y0, c1 = Y2
+    bfly2(c2, c3);              // c2 = Y1, c3 = Y3
+    const double2 t = c1; c1 = c2; c2 = t;
 }
 
 // 8-point forward DFT in place (natural order out).
 SIMT_HD void dft8(double2 (&a)[8]) {
     const double h = 0.70710678118654752440;
-    double2 b0 = cadd(a[0], a[4]), b4 = csub(a[0], a[4]);
-    double2 b1 = cadd(a[1], a[5]), b5 = csub(a[1], a[5]);
-    double2 b2 = cadd(a[2], a[6]), b6 = csub(a[2], a[6]);
-    double2 b3 = cadd(a[3], a[7]), b7 = csub(a[3], a[7]);
+    bfly2(a[0], a[4]);
+    bfly2(a[1], a[5]);
+    bfly2(a[2], a[6]);
+    bfly2(a[3], a[7]);
     // odd branch twiddles W8^1 = (1-i)/sqrt2, W8^2 = -i, W8^3 = (-1-i)/sqrt2
-    b5 = make_double2((b5.x + b5.y) * h, (b5.y - b5.x) * h);
-    b6 = cmul_mi(b6);
-    b7 = make_double2((b7.y - b7.x) * h, -(b7.x + b7.y) * h);
-    dft4(b0, b1, b2, b3);
-    dft4(b4, b5, b6, b7);
-    a[0] = b0; a[2] = b1; a[4] = b2; a[6] = b3;
-    a[1] = b4; a[3] = b5; a[5] = b6; a[7] = b7;
+    a[5] = make_double2((a[5].x + a[5].y) * h, (a[5].y - a[5].x) * h);
+    a[6] = cmul_mi(a[6]);
+    a[7] = make_double2((a[7].y - a[7].x) * h, -(a[7].x + a[7].y) * h);
+    dft4(a[0], a[1], a[2], a[3]);     // X0 X2 X4 X6
+    dft4(a[4], a[5], a[6], a[7]);     // X1 X3 X5 X7
+    double2 t;
+    // permute (X0 X2 X4 X6 X1 X3 X5 X7) -> natural order
+    t = a[1]; a[1] = a[4]; a[4] = a[2]; a[2] = t;      // a1 = X1, a4 = X4, a2 = X2
+    t = a[3]; a[3] = a[5]; a[5] = a[6]; a[6] = t;      // a3 = X3, a5 = X5, a6 = X6
 }
 
-// Shared-memory view of one complex line among L side-by-side lines.
+// Shared-memory view of one complex line among L = 2^lgL side-by-side lines.
 struct LineView {
-    double2* sm;   // base of the unit's buffer (L*n chunks)
-    int L, l;      // lines side by side, my line
-    SIMT_DEVICE double2& at(int k) const { return sm[swz(k * L + l)]; }
+    double2* sm;     // base of the unit's buffer (L*n chunks)
+    int lgL, l;
+    SIMT_DEVICE double2& at(int k) const { return sm[swz((k << lgL) | l)]; }
 };
 
 // Forward FFT of the line whose elements the calling threads hold in v (v[m] = x[lt + m*n/8]).
 // On return the line sits in shared memory in natural order (all threads have passed the final
 // barrier).  EVERY thread of the block must call this (uniform barriers); threads whose unit is
 // out of range pass valid = false and only take part in the barriers.
-// n >= 8, power of two; tw[k] = exp(-2 pi i k / n), k < n.
-SIMT_DEVICE void fft_line_forward(double2 (&v)[8], const LineView& lv, int lt, int n, int log2n,
+// n = 2^log2n >= 8; tw[k] = exp(-2 pi i k / n), k < n.
+SIMT_DEVICE void fft_line_forward(double2 (&v)[8], const LineView& lv, int lt, int log2n,
                                   const double2* __restrict__ tw, bool valid) {
-    const int n8 = n >> 3;
-    int Ns = 1;
+    const int n8 = 1 << (log2n - 3);
     const int lead = log2n % 3;   // 0: all radix-8; 1: leading radix-2; 2: leading radix-4
-    bool first = true;
-    while (Ns < n) {
-        const int R = (first && lead == 1) ? 2 : ((first && lead == 2) ? 4 : 8);
+    int lgNs = 0;
+    if (lead == 2) {
+        // leading radix-4 stage (Ns = 1): two butterflies j = lt + q*n8, inputs v[q + 2t]
         if (valid) {
-            if (R == 8) {
-                const int j = lt;
-                if (Ns > 1) {
-                    const int tstride = n / (Ns * 8);
-                    const int jm = (j & (Ns - 1)) * tstride;
 #pragma unroll
-                    for (int t = 1; t < 8; ++t) v[t] = cmul(v[t], SIMT_LDG(&tw[jm * t]));
-                }
-                dft8(v);
-                const int base = (j / Ns) * Ns * 8 + (j & (Ns - 1));
+            for (int q = 0; q < 2; ++q) {
+                dft4(v[q], v[q + 2], v[q + 4], v[q + 6]);
+                const int j4 = (lt + q * n8) << 2;
 #pragma unroll
-                for (int t = 0; t < 8; ++t) lv.at(base + t * Ns) = v[t];
-            } else if (R == 4) {
-                // two butterflies: j = lt + q*n8, inputs v[q + 2t] (always the leading stage: Ns = 1)
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    dft4(v[q], v[q + 2], v[q + 4], v[q + 6]);
-                    const int j = lt + q * n8;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) lv.at(j * 4 + t) = v[q + 2 * t];
-                }
-            } else {
-                // four butterflies: j = lt + q*n8, inputs v[q], v[q + 4] (leading stage: Ns = 1)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    double2 s = cadd(v[q], v[q + 4]), d = csub(v[q], v[q + 4]);
-                    const int j = lt + q * n8;
-                    lv.at(j * 2) = s;
-                    lv.at(j * 2 + 1) = d;
-                }
+                for (int t = 0; t < 4; ++t) lv.at(j4 + t) = v[q + 2 * t];
             }
+        }
+        lgNs = 2;
+    } else if (lead == 1) {
+        // leading radix-2 stage (Ns = 1): four butterflies j = lt + q*n8, inputs v[q], v[q + 4]
+        if (valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                bfly2(v[q], v[q + 4]);
+                const int j2 = (lt + q * n8) << 1;
+                lv.at(j2) = v[q];
+                lv.at(j2 + 1) = v[q + 4];
+            }
+        }
+        lgNs = 1;
+    }
+    if (lead != 0) {
+        SIMT_SYNC();
+        if (valid) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) v[m] = lv.at(lt + m * n8);
         }
         SIMT_SYNC();
-        Ns *= R;
-        first = false;
-        if (Ns < n) {
-            if (valid) {
-#pragma unroll
-                for (int m = 0; m < 8; ++m) v[m] = lv.at(lt + m * n8);
+    }
+    // radix-8 stages
+    while (true) {
+        if (valid) {
+            const int jlo = lt & ((1 << lgNs) - 1);
+            if (lgNs > 0) {
+                // twiddles W^(jlo*t), W = exp(-2 pi i / (8 Ns)): three table loads, the rest by products
+                const int jm = jlo << (log2n - 3 - lgNs);
+                const double2 w1 = SIMT_LDG(&tw[jm]);
+                const double2 w2 = SIMT_LDG(&tw[2 * jm]);
+                const double2 w4 = SIMT_LDG(&tw[4 * jm]);
+                v[1] = cmul(v[1], w1);
+                v[2] = cmul(v[2], w2);
+                v[4] = cmul(v[4], w4);
+                double2 w = cmul(w1, w2);         // W^3
+                v[3] = cmul(v[3], w);
+                w = cmul(w, w4);                  // W^7
+                v[7] = cmul(v[7], w);
+                w = cmul(w1, w4);                 // W^5
+                v[5] = cmul(v[5], w);
+                w = cmul(w2, w4);                 // W^6
+                v[6] = cmul(v[6], w);
             }
-            SIMT_SYNC();
+            dft8(v);
+            const int base = ((lt >> lgNs) << (lgNs + 3)) | jlo;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) lv.at(base + (t << lgNs)) = v[t];
         }
+        SIMT_SYNC();
+        lgNs += 3;
+        if (lgNs >= log2n) break;
+        if (valid) {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) v[m] = lv.at(lt + m * n8);
+        }
+        SIMT_SYNC();
     }
 }
 
 // After fft_line_forward: v[m] <- 2 * ( H(a)[k], H(b)[k] ), k = lt + m*n/8.
 // (The factor 2 is folded into the callers' scale constants; powers of two are exact.)
-SIMT_DEVICE void dht_combine_read(double2 (&v)[8], const LineView& lv, int lt, int n) {
-    const int n8 = n >> 3;
+SIMT_DEVICE void dht_combine_read(double2 (&v)[8], const LineView& lv, int lt, int log2n) {
+    const int n8 = 1 << (log2n - 3);
+    const int nmask = (1 << log2n) - 1;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
         const int k = lt + m * n8;
         const double2 zk = lv.at(k);
-        const double2 zn = lv.at((n - k) & (n - 1));
+        const double2 zn = lv.at((-k) & nmask);
         v[m] = make_double2(zk.x - zk.y + zn.x + zn.y, zk.x + zk.y + zn.y - zn.x);
     }
 }

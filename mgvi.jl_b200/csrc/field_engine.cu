@@ -16,6 +16,9 @@ SIMT_GLOBAL(256) k_naive_axis(SIMT_KARGS(NaiveParams)) {
 
 namespace {
 
+#ifndef MGVI_MINB
+#define MGVI_MINB 3      // resident 256-thread blocks per SM the pass kernels are compiled for
+#endif
 const int kNaiveMaxAxis = 4096;
 const long long kFastMaxAxis = 4096;
 
@@ -23,7 +26,7 @@ bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
 int ilog2(long long v) { int l = 0; while ((1LL << l) < v) ++l; return l; }
 
 struct PassGeo {
-    int geo, n, log2n, L, G, threads;
+    int geo, n, log2n, L, G, threads, lgL, lg_tpo;
     long long inner, units_per_vec, ntb;
     size_t smem;
 };
@@ -88,6 +91,7 @@ struct FieldEngine : Engine {
         fast = true;
         for (int i = 0; i < ndim; ++i)
             if (!is_pow2(dims[i]) || dims[i] < 8 || dims[i] > kFastMaxAxis) fast = false;
+        if (N >= (1LL << 31)) fast = false;      // the pass kernels use 32-bit element offsets
         if (const char* e = getenv("MGVIB200_FORCE_GENERIC")) if (atoi(e)) fast = false;
         if (const char* e = getenv("MGVIB200_STRIDED_L")) max_L = std::max(1, atoi(e));
         if (!fast)
@@ -186,12 +190,15 @@ struct FieldEngine : Engine {
         }
         g.threads = g.G * g.L * tpl;
         g.smem = (size_t)field_pass_smem_bytes(g.n, g.L, g.G);
+        g.lgL = ilog2(g.L);
+        g.lg_tpo = (g.geo == GEO_STRIDED) ? ilog2(g.inner / (2 * g.L)) : 0;
         return g;
     }
 
-    template <int PRO, int EPI, bool DBL>
+    template <int GEO, int PRO, int EPI, bool DBL>
     void launch_pass(FieldPassParams P, const PassGeo& g, int nvec, int nsgrp, int nloop) {
-        P.geo = g.geo; P.n = g.n; P.log2n = g.log2n; P.L = g.L; P.G = g.G;
+        if (g.geo != GEO) throw RtError{"internal: geometry class mismatch", 1};
+        P.geo = g.geo; P.n = g.n; P.log2n = g.log2n; P.L = g.L; P.G = g.G; P.lgL = g.lgL; P.lg_tpo = g.lg_tpo;
         P.N = N; P.inner = g.inner; P.units_per_vec = g.units_per_vec; P.ntb = g.ntb;
         P.nvec = nvec; P.nsgrp = nsgrp; P.nloop = nloop;
         P.tw = tw.at(g.n).as<double2>();
@@ -208,10 +215,14 @@ struct FieldEngine : Engine {
             P.partials = rws.partials.as<double>();
             P.counters = rws.counters.as<unsigned>();
         }
+        ctx->prof_pre(PRO * 100 + EPI * 10 + (DBL ? 1 : 0));
         if (g.threads <= 256)
-            rt_launch(k_field_pass<PRO, EPI, DBL, 256>, grid, g.threads, g.smem, ctx->stream, P);
+            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 256, MGVI_MINB>, grid, g.threads, g.smem, ctx->stream, P);
+        else if (g.threads <= 512)
+            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 512, 1>, grid, g.threads, g.smem, ctx->stream, P);
         else
-            rt_launch(k_field_pass<PRO, EPI, DBL, 1024>, grid, g.threads, g.smem, ctx->stream, P);
+            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 1024, 1>, grid, g.threads, g.smem, ctx->stream, P);
+        ctx->prof_post();
         ctx->launches++;
     }
 
@@ -310,19 +321,19 @@ struct FieldEngine : Engine {
             }
             P.fin = (fin_epi != FIN_NONE) ? fin_epi : fin_pro;
             P.red_out = (fin_epi != FIN_NONE) ? red_epi : red_pro;
-            launch_pass<PRO, EPI, false>(P, g, nvec, nsgrp, nloop);
+            launch_pass<GEO_PAIRVEC, PRO, EPI, false>(P, g, nvec, nsgrp, nloop);
             return chunks;
         }
         // contiguous axis first
         {
             FieldPassParams Q = P;
             Q.out = scratch; Q.out_ld = N; Q.fin = fin_pro; Q.red_out = red_pro;
-            launch_pass<PRO, EPI_STORE, false>(Q, geo_axis(ndim - 1, nvec), nvec, nvec, 1);
+            launch_pass<GEO_CONTIG, PRO, EPI_STORE, false>(Q, geo_axis(ndim - 1, nvec), nvec, nvec, 1);
         }
         for (int a = ndim - 2; a >= 1; --a) {
             FieldPassParams Q = P;
             Q.in = scratch; Q.in_ld = N; Q.out = scratch; Q.out_ld = N; Q.fin = FIN_NONE;
-            launch_pass<PRO_LOAD, EPI_STORE, false>(Q, geo_axis(a, nvec), nvec, nvec, 1);
+            launch_pass<GEO_STRIDED, PRO_LOAD, EPI_STORE, false>(Q, geo_axis(a, nvec), nvec, nvec, 1);
         }
         {
             FieldPassParams Q = P;
@@ -335,7 +346,7 @@ struct FieldEngine : Engine {
                 acc.ensure(sizeof(double) * N * chunks);
                 Q.acc_out = acc.as<double>();
             }
-            launch_pass<PRO_LOAD, EPI, false>(Q, g, nvec, nsgrp, nloop);
+            launch_pass<GEO_STRIDED, PRO_LOAD, EPI, false>(Q, g, nvec, nsgrp, nloop);
             return chunks;
         }
     }
@@ -348,23 +359,23 @@ struct FieldEngine : Engine {
         }
         if (ndim == 1) {
             P.fin = fin_epi; P.red_out = red_epi;
-            launch_pass<PRO, EPI, false>(P, geo_axis(0, nvec), nvec, 1, 1);
+            launch_pass<GEO_PAIRVEC, PRO, EPI, false>(P, geo_axis(0, nvec), nvec, 1, 1);
             return;
         }
         {
             FieldPassParams Q = P;
             Q.out = scratch; Q.out_ld = N; Q.fin = FIN_NONE;
-            launch_pass<PRO, EPI_STORE, false>(Q, geo_axis(0, nvec), nvec, nvec, 1);
+            launch_pass<GEO_STRIDED, PRO, EPI_STORE, false>(Q, geo_axis(0, nvec), nvec, nvec, 1);
         }
         for (int a = 1; a <= ndim - 2; ++a) {
             FieldPassParams Q = P;
             Q.in = scratch; Q.in_ld = N; Q.out = scratch; Q.out_ld = N; Q.fin = FIN_NONE;
-            launch_pass<PRO_LOAD, EPI_STORE, false>(Q, geo_axis(a, nvec), nvec, nvec, 1);
+            launch_pass<GEO_STRIDED, PRO_LOAD, EPI_STORE, false>(Q, geo_axis(a, nvec), nvec, nvec, 1);
         }
         {
             FieldPassParams Q = P;
             Q.in = scratch; Q.in_ld = N; Q.fin = fin_epi; Q.red_out = red_epi;
-            launch_pass<PRO_LOAD, EPI, false>(Q, geo_axis(ndim - 1, nvec), nvec, nvec, 1);
+            launch_pass<GEO_CONTIG, PRO_LOAD, EPI, false>(Q, geo_axis(ndim - 1, nvec), nvec, nvec, 1);
         }
     }
 
@@ -378,23 +389,23 @@ struct FieldEngine : Engine {
         }
         if (ndim == 1) {
             P.fin = fin; P.red_out = red;
-            launch_pass<PRO, EPI_METRIC, true>(P, geo_axis(0, nvec), nvec, 1, 1);
+            launch_pass<GEO_PAIRVEC, PRO, EPI_METRIC, true>(P, geo_axis(0, nvec), nvec, 1, 1);
             return;
         }
         {
             FieldPassParams Q = P;
             Q.out = scratch; Q.out_ld = N; Q.fin = FIN_NONE;
-            launch_pass<PRO, EPI_STORE, false>(Q, geo_axis(ndim - 1, nvec), nvec, nvec, 1);
+            launch_pass<GEO_CONTIG, PRO, EPI_STORE, false>(Q, geo_axis(ndim - 1, nvec), nvec, nvec, 1);
         }
         FieldPassParams S = P;
         S.in = scratch; S.in_ld = N; S.out = scratch; S.out_ld = N; S.fin = FIN_NONE;
-        for (int a = ndim - 2; a >= 1; --a) launch_pass<PRO_LOAD, EPI_STORE, false>(S, geo_axis(a, nvec), nvec, nvec, 1);
-        launch_pass<PRO_LOAD, EPI_STORE, true>(S, geo_axis(0, nvec), nvec, nvec, 1);
-        for (int a = 1; a <= ndim - 2; ++a) launch_pass<PRO_LOAD, EPI_STORE, false>(S, geo_axis(a, nvec), nvec, nvec, 1);
+        for (int a = ndim - 2; a >= 1; --a) launch_pass<GEO_STRIDED, PRO_LOAD, EPI_STORE, false>(S, geo_axis(a, nvec), nvec, nvec, 1);
+        launch_pass<GEO_STRIDED, PRO_LOAD, EPI_STORE, true>(S, geo_axis(0, nvec), nvec, nvec, 1);
+        for (int a = 1; a <= ndim - 2; ++a) launch_pass<GEO_STRIDED, PRO_LOAD, EPI_STORE, false>(S, geo_axis(a, nvec), nvec, nvec, 1);
         {
             FieldPassParams Q = P;
             Q.in = scratch; Q.in_ld = N; Q.fin = fin; Q.red_out = red;
-            launch_pass<PRO_LOAD, EPI_METRIC, false>(Q, geo_axis(ndim - 1, nvec), nvec, nvec, 1);
+            launch_pass<GEO_CONTIG, PRO_LOAD, EPI_METRIC, false>(Q, geo_axis(ndim - 1, nvec), nvec, nvec, 1);
         }
     }
 

@@ -45,7 +45,7 @@ struct CgScalars {
 
 struct FieldPassParams {
     // ---- geometry -------------------------------------------------------------------------
-    int geo, n, log2n, L, G;
+    int geo, n, log2n, L, G, lgL, lg_tpo;
     long long N, inner, units_per_vec, ntb;
     int nvec, nsgrp, nloop;
     const double2* tw;
@@ -330,27 +330,34 @@ SIMT_HD long long field_pass_smem_bytes(int n, int L, int G) {
     return kSmemHeader + (long long)G * L * n * 16;
 }
 
-template <int PRO, int EPI, bool DOUBLE>
+// GEO is a compile-time geometry class:
+//   GEO_CONTIG : lines along the last (contiguous) axis; a unit = two neighbouring rows of one vector
+//   GEO_STRIDED: lines along an outer axis; a unit = a tile of 2L neighbouring columns
+//   GEO_PAIRVEC: 1-D fields; a unit = two vectors
+// All sizes are powers of two, so thread/unit decoding is shifts and masks.  Element offsets
+// inside a vector are 32-bit (N < 2^31, checked on the host).
+template <int GEO, int PRO, int EPI, bool DOUBLE>
 SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_raw) {
-    const int n = P.n, n8 = n >> 3, L = P.L;
+    const int log2n = P.log2n, lgL = P.lgL;
+    const int n8 = 1 << (log2n - 3);
     const int tid = SIMT_TID;
-    const int upt = n8 * L;                 // threads per unit
-    const int g = tid / upt;
-    const int tu = tid - g * upt;
-    const int l = tu % L, lt = tu / L;
+    const int lg_upt = log2n - 3 + lgL;          // threads per unit = 2^lg_upt
+    const int g = tid >> lg_upt;
+    const int tu = tid & ((1 << lg_upt) - 1);
+    const int l = tu & ((1 << lgL) - 1), lt = tu >> lgL;
     double* red = reinterpret_cast<double*>(smem_raw);
     int* flag = reinterpret_cast<int*>(smem_raw + 256);
     LineView lv;
-    lv.sm = reinterpret_cast<double2*>(smem_raw + kSmemHeader) + (long long)g * L * n;
-    lv.L = L;
+    lv.sm = reinterpret_cast<double2*>(smem_raw + kSmemHeader) + ((long long)g << (lgL + log2n));
+    lv.lgL = lgL;
     lv.l = l;
 
-    const bool pairvec = (P.geo == GEO_PAIRVEC);
-    const bool adj = (P.geo == GEO_STRIDED);
+    const bool pairvec = (GEO == GEO_PAIRVEC);
+    const bool adj = (GEO == GEO_STRIDED);
     long long bt;
     int sgrp;
     if (pairvec) { bt = SIMT_BID; sgrp = 0; }
-    else { bt = SIMT_BID / P.nsgrp; sgrp = (int)(SIMT_BID % P.nsgrp); }
+    else { bt = SIMT_BID / P.nsgrp; sgrp = (int)(SIMT_BID - bt * P.nsgrp); }
     const bool use_active = (P.mask_active != 0);
     if (use_active && !pairvec && P.nloop == 1) {
         if (!P.cg.active[sgrp]) return;    // uniform for the whole block
@@ -358,20 +365,28 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
 
     double acc_a = 0.0, acc_b = 0.0;
     double2 accv[8];
+    if (EPI == EPI_KL || EPI == EPI_LINEARIZE) {
 #pragma unroll
-    for (int m = 0; m < 8; ++m) accv[m] = make_double2(0.0, 0.0);
-    long long base_a = 0, base_b = 0, stride = 1;
+        for (int m = 0; m < 8; ++m) accv[m] = make_double2(0.0, 0.0);
+    }
+    // element offsets of my 8 elements: off_a + m * step (and off_b + m * step)
+    unsigned off_a = 0, off_b = 0, step = (unsigned)n8;
     bool unit_ok = true;
     if (!pairvec) {
         const long long u = bt * P.G + g;
         unit_ok = u < P.units_per_vec;
-        if (P.geo == GEO_CONTIG) {
-            base_a = 2 * u * n; base_b = base_a + n; stride = 1;
+        if (GEO == GEO_CONTIG) {
+            off_a = (unsigned)((2 * u) << log2n) + (unsigned)lt;
+            off_b = off_a + (1u << log2n);
+            step = (unsigned)n8;
         } else {
-            const long long tpo = P.inner / (2 * L);
-            const long long o = u / tpo, cb = u - o * tpo;
-            base_a = o * n * P.inner + cb * 2 * L + 2 * l; base_b = base_a + 1; stride = P.inner;
+            const long long o = u >> P.lg_tpo, cb = u & ((1LL << P.lg_tpo) - 1);
+            off_a = (unsigned)(((o << log2n) + lt) * P.inner + (cb << (lgL + 1)) + 2 * l);
+            off_b = off_a + 1;
+            step = (unsigned)(n8 * P.inner);
         }
+    } else {
+        off_a = off_b = (unsigned)lt;
     }
     int sa = 0, sb = 0;
     bool va = false, vb = false;
@@ -392,34 +407,28 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
         double2 v[8];
         if (valid) {
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const long long k = lt + m * n8;
-                v[m] = pro_pair<PRO>(P, sa, sb, base_a + k * stride, base_b + k * stride, va, vb, adj, acc_a, acc_b);
-            }
+            for (int m = 0; m < 8; ++m)
+                v[m] = pro_pair<PRO>(P, sa, sb, off_a + m * step, off_b + m * step, va, vb, adj, acc_a, acc_b);
         }
         if (it > 0) SIMT_SYNC();   // previous iteration's combine reads vs this iteration's writes
-        fft_line_forward(v, lv, lt, n, P.log2n, P.tw, valid);
-        if (valid) dht_combine_read(v, lv, lt, n);
+        fft_line_forward(v, lv, lt, log2n, P.tw, valid);
+        if (valid) dht_combine_read(v, lv, lt, log2n);
         if (DOUBLE) {
             if (valid) {
 #pragma unroll
                 for (int m = 0; m < 8; ++m) {
-                    const long long k = lt + m * n8;
-                    double2 wv = ldg_pair(P.w, base_a + k * stride, base_b + k * stride, va, vb, adj);
+                    double2 wv = ldg_pair(P.w, off_a + m * step, off_b + m * step, va, vb, adj);
                     v[m] = make_double2(v[m].x * wv.x, v[m].y * wv.y);
                 }
             }
             SIMT_SYNC();
-            fft_line_forward(v, lv, lt, n, P.log2n, P.tw, valid);
-            if (valid) dht_combine_read(v, lv, lt, n);
+            fft_line_forward(v, lv, lt, log2n, P.tw, valid);
+            if (valid) dht_combine_read(v, lv, lt, log2n);
         }
         if (valid) {
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const long long k = lt + m * n8;
-                epi_pair<EPI>(P, sa, sb, base_a + k * stride, base_b + k * stride, va, vb, adj, v[m], acc_a, acc_b,
-                              accv[m]);
-            }
+            for (int m = 0; m < 8; ++m)
+                epi_pair<EPI>(P, sa, sb, off_a + m * step, off_b + m * step, va, vb, adj, v[m], acc_a, acc_b, accv[m]);
         }
     }
     // ---- accumulated per-element outputs ---------------------------------------------------
@@ -427,14 +436,11 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
         if (pairvec) {
             const long long chunk = bt * P.G + g;
 #pragma unroll
-            for (int m = 0; m < 8; ++m) P.acc_out[chunk * P.N + lt + m * n8] = accv[m].x + accv[m].y;
+            for (int m = 0; m < 8; ++m) P.acc_out[chunk * P.N + off_a + m * step] = accv[m].x + accv[m].y;
         } else if (unit_ok) {
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const long long k = lt + m * n8;
-                st_pair(P.acc_out + (long long)sgrp * P.N, base_a + k * stride, base_b + k * stride, true, true, adj,
-                        accv[m]);
-            }
+            for (int m = 0; m < 8; ++m)
+                st_pair(P.acc_out + (long long)sgrp * P.N, off_a + m * step, off_b + m * step, true, true, adj, accv[m]);
         }
     }
     // ---- scalar reductions -----------------------------------------------------------------
@@ -445,9 +451,9 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
                                    flag);
     } else if (pairvec) {
         // every vector lives entirely inside one unit (nloop == 1 for per-vector reductions)
-        const double ta = seg_reduce(acc_a, upt, red);
+        const double ta = seg_reduce(acc_a, 1 << lg_upt, red);
         SIMT_SYNC();
-        const double tb = seg_reduce(acc_b, upt, red);
+        const double tb = seg_reduce(acc_b, 1 << lg_upt, red);
         if (tu == 0) {
             if (va) finalize_vec(P.fin, P.cg, P.red_out, sa, ta);
             if (vb) finalize_vec(P.fin, P.cg, P.red_out, sb, tb);

@@ -14,10 +14,17 @@
 
 namespace mgvi {
 
-template <int PRO, int EPI, bool DOUBLE, int MAXT>
-SIMT_GLOBAL(MAXT) k_field_pass(SIMT_KARGS(FieldPassParams)) {
+#if defined(__CUDACC__) && !defined(MGVI_SIMT_EMU)
+#define SIMT_GLOBAL2(maxt, minb) __global__ void __launch_bounds__(maxt, minb)
+#else
+#define SIMT_GLOBAL2(maxt, minb) static void
+#endif
+
+// MAXT = 256: up to 256 threads, MINB resident blocks per SM wanted; MAXT = 1024: wide tiles.
+template <int GEO, int PRO, int EPI, bool DOUBLE, int MAXT, int MINB>
+SIMT_GLOBAL2(MAXT, MINB) k_field_pass(SIMT_KARGS(FieldPassParams)) {
     SIMT_SMEM_DECL
-    field_pass_body<PRO, EPI, DOUBLE>(P, simt_smem);
+    field_pass_body<GEO, PRO, EPI, DOUBLE>(P, simt_smem);
 }
 
 template <int PRO>

@@ -33,7 +33,9 @@ void vec_launch(mgvib200_ctx* ctx, ReduceWs& ws, VecParams P) {
         P.counters = ws.counters.as<unsigned>();
         if (!P.red_out) P.red_out = ws.red.as<double>();
     }
+    ctx->prof_pre(1000 + P.op);
     rt_launch(k_vec, grid, kVecThreads, 512, ctx->stream, P);
+    ctx->prof_post();
     ctx->launches++;
 }
 

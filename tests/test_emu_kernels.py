@@ -111,3 +111,16 @@ def test_single_residual_and_rng_draws(pkg, emu_ctx):
     b = pkg.sample_residuals(s, 2)
     np.testing.assert_array_equal(a, b)
     m.close()
+
+
+@pytest.mark.parametrize("layout", [1, 2])
+def test_polyfit_reference_model(pkg, emu_ctx, layout):
+    """BASELINE.json configs[0] on the reference's own 40-point grids (model_polyfit.jl:11-12)."""
+    from helpers import check_poly_ops
+    cfg = pkg.synthetic.polyfit_config(4, reference_grid=True, layout=layout)
+    out = check_poly_ops(pkg, emu_ctx, cfg)
+    for k in ("metric", "fisher", "dense", "kl", "grad", "mean_metric"):
+        assert out[k] < 1e-9, (k, out)      # the 5x5 metric has condition number ~1e7
+    assert out["iters_default"][0] == out["iters_default"][1] == [5] * 4
+    assert out["residuals"] < 1e-8, out
+    assert out["cg_step"] < 1e-8 and out["dense_step"] < 1e-9, out

@@ -1,0 +1,188 @@
+"""Parity of the CUDA path (product library, through the C ABI, cuda:0) against the oracle.
+
+Tolerance: relative 1e-10 in Float64 on M.v, CG solutions and the updated mean (BASELINE.json
+north_star), CG stopping rule tightened to reltol 1e-12 / abstol 0 on both sides;
+bit-exact sample ordering and antithetic pairing.  At BASELINE.json's full sizes the oracle is
+used where it finishes in seconds (one metric product) and size-independent properties
+elsewhere (symmetry of M, H.H = N I, residual of the CG solution)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from golden_io import load_golden
+from helpers import RTOL, TIGHT, assert_field_ops, assert_step_parity, check_field_ops, oracle_model, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _field(pkg, dims, like, n, layout=None, std=0.5, **kw):
+    syn = pkg.synthetic
+    return syn.field_config(dims, getattr(syn, like), n, field_std=std, layout=layout, **kw)
+
+
+def test_native_library_is_loaded(pkg, gpu_ctx):
+    assert gpu_ctx.lib.path.endswith("libmgvib200.so")
+    assert b"sm_100a" in gpu_ctx.lib.version()
+    maps = open("/proc/self/maps").read()
+    assert "libmgvib200.so" in maps
+
+
+@pytest.mark.parametrize("n", [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096])
+def test_metric_1d_every_length(pkg, gpu_ctx, n):
+    cfg = _field(pkg, (n,), "LIKE_POISSON", 5)
+    m = pkg.model_from_config(cfg, gpu_ctx)
+    om = oracle_model(cfg)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(**TIGHT), gpu_ctx)
+    lin = om.linearize(cfg["center"])
+    V = np.random.default_rng(5).standard_normal((n, 5))
+    MVo = np.stack([O.metric_apply(lin, V[:, i]) for i in range(5)], axis=1)
+    assert rel(s.metric_apply(V), MVo) < RTOL
+    m.close()
+
+
+@pytest.mark.parametrize("dims,like,layout,n", [
+    ((4096,), "LIKE_POISSON", None, 4),
+    ((256, 256), "LIKE_NORMAL", 1, 4),
+    ((128, 512), "LIKE_POISSON", None, 3),
+    ((8, 2048), "LIKE_NORMAL", 2, 2),
+    ((2048, 8), "LIKE_POISSON", None, 2),
+    ((32, 64, 16), "LIKE_POISSON", None, 3),
+    ((16, 8, 128), "LIKE_NORMAL", 0, 2),
+    ((40,), "LIKE_NORMAL", 2, 4),          # reference fixture length, generic path
+    ((30, 50), "LIKE_POISSON", None, 3),   # non power of two 2-D, generic path
+])
+def test_field_ops_vs_oracle(pkg, gpu_ctx, dims, like, layout, n):
+    cfg = _field(pkg, dims, like, n, layout)
+    assert_field_ops(check_field_ops(pkg, gpu_ctx, cfg, check_step=True), cfg)
+
+
+def test_identity_link(pkg, gpu_ctx):
+    syn = pkg.synthetic
+    cfg = syn.field_config((64, 64), syn.LIKE_NORMAL, 3, field_std=0.5)
+    cfg["link"] = syn.LINK_IDENTITY
+    assert_field_ops(check_field_ops(pkg, gpu_ctx, cfg, check_step=True), cfg)
+
+
+@pytest.mark.parametrize("name", ["fft_gp_40", "field_1d_64_poisson", "field_2d_16x32_normal",
+                                  "field_3d_8x8x16_poisson"])
+def test_golden_vectors(pkg, gpu_ctx, name):
+    cfg, gold = load_golden(name)
+    m = pkg.model_from_config(cfg, gpu_ctx)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(**TIGHT), gpu_ctx)
+    assert rel(s.metric_apply(gold["V"]), gold["MV"]) < RTOL
+    R = pkg.sample_residuals(s, cfg["n_residuals"], draws=(cfg["Z1"], cfg["Z2"]))
+    assert rel(R, gold["R"]) < RTOL
+    f, g = pkg.kl_value_grad(m, cfg["center"], gold["R"])
+    assert abs(f - gold["f"]) / abs(gold["f"]) < RTOL and rel(g, gold["grad"]) < RTOL
+    res, c = pkg.mgvi_step(m, cfg["data"], cfg["n_residuals"], cfg["center"],
+                           pkg.MGVIConfig(linsolver=pkg.B200CG(**TIGHT)), gpu_ctx, draws=(cfg["Z1"], cfg["Z2"]))
+    tr = res.info["optimizer_output"]
+    trace_equal = (tr["cg_updates"] == gold["tr_cg_updates"].tolist() and tr["f_calls"] == int(gold["tr_f_calls"]))
+    assert_step_parity(cfg, rel(c, gold["step_center"]), rel(res.samples, gold["step_samples"]), trace_equal)
+    assert rel(res.samples[:, 0::2] - res.samples[:, 1::2],
+               gold["step_samples"][:, 0::2] - gold["step_samples"][:, 1::2]) < RTOL
+    m.close()
+
+
+def test_default_tolerance_iteration_counts(pkg, gpu_ctx):
+    cfg = _field(pkg, (128, 128), "LIKE_POISSON", 4)
+    m = pkg.model_from_config(cfg, gpu_ctx)
+    om = oracle_model(cfg)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(), gpu_ctx)
+    R, info = pkg.sample_residuals(s, 4, draws=(cfg["Z1"], cfg["Z2"]), return_info=True)
+    Ro, ito, rno = O.sample_residuals_cg(om, cfg["center"], cfg["Z1"], cfg["Z2"])
+    assert np.abs(info["iters"] - ito).max() <= 2, (info["iters"], ito)
+    assert rel(R, Ro) < 1e-6          # both stop at ||r|| ~ 1.5e-8 (1 + ||b||)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(abstol=0.0, reltol=0.0, maxiters=9), gpu_ctx)
+    R, info = pkg.sample_residuals(s, 4, draws=(cfg["Z1"], cfg["Z2"]), return_info=True)
+    Ro, ito, _ = O.sample_residuals_cg(om, cfg["center"], cfg["Z1"], cfg["Z2"], atol=0.0, rtol=0.0, itmax=9)
+    assert info["iters"].tolist() == [9] * 4 == ito.tolist()
+    assert rel(R, Ro) < RTOL
+    m.close()
+
+
+def test_many_residuals_lockstep_masking(pkg, gpu_ctx):
+    """33 residuals (odd count) with very different right-hand-side scales converge at different
+    iterations; every one must match its own independent oracle solve."""
+    cfg = _field(pkg, (64, 32), "LIKE_POISSON", 33)
+    scale = np.logspace(-6, 3, 33)
+    cfg["Z1"] = cfg["Z1"] * scale
+    cfg["Z2"] = cfg["Z2"] * scale
+    m = pkg.model_from_config(cfg, gpu_ctx)
+    om = oracle_model(cfg)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(abstol=1e-9, reltol=1e-12), gpu_ctx)
+    R, info = pkg.sample_residuals(s, 33, draws=(cfg["Z1"], cfg["Z2"]), return_info=True)
+    Ro, ito, _ = O.sample_residuals_cg(om, cfg["center"], cfg["Z1"], cfg["Z2"], atol=1e-9, rtol=1e-12)
+    assert len(set(info["iters"].tolist())) > 3
+    assert np.abs(info["iters"] - ito).max() <= 2
+    for i in range(33):
+        assert np.linalg.norm(R[:, i] - Ro[:, i]) <= 1e-8 * np.linalg.norm(Ro[:, i]) + 2e-9, i
+    m.close()
+
+
+# ---- BASELINE.json full sizes -------------------------------------------------------------------
+def _full_metric_checks(pkg, gpu_ctx, cfg, n_solve):
+    m = pkg.model_from_config(cfg, gpu_ctx)
+    om = oracle_model(cfg)
+    c = cfg["center"]
+    s = pkg.ResidualSampler(m, c, pkg.B200CG(abstol=0.0, reltol=1e-10), gpu_ctx)
+    lin = om.linearize(c)
+    rng = np.random.default_rng(5)
+    V = rng.standard_normal((m.n_theta, 2))
+    MV = s.metric_apply(V)
+    # direct parity with the oracle on one product (the oracle needs ~1 s at this size)
+    assert rel(MV[:, 0], O.metric_apply(lin, V[:, 0])) < RTOL
+    # symmetry <u, M v> = <M u, v> and M >= I
+    a, b = float(V[:, 0] @ MV[:, 1]), float(MV[:, 0] @ V[:, 1])
+    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b), np.linalg.norm(V[:, 0]) * np.linalg.norm(MV[:, 1]))
+    assert float(V[:, 0] @ MV[:, 0]) >= float(V[:, 0] @ V[:, 0])
+    # CG solutions satisfy M x = b (b rebuilt by the oracle from the same draws)
+    Z1 = np.asfortranarray(cfg["Z1"][:, :n_solve])
+    Z2 = np.asfortranarray(cfg["Z2"][:, :n_solve])
+    R, info = pkg.sample_residuals(s, n_solve, draws=(Z1, Z2), return_info=True)
+    for i in range(n_solve):
+        bvec = O.sampler_rhs(lin, Z1[:, i], Z2[:, i])
+        res = O.metric_apply(lin, R[:, i]) - bvec
+        assert np.linalg.norm(res) <= 2e-10 * np.linalg.norm(bvec), (i, info)
+    m.close()
+    return info
+
+
+def test_full_size_c3_2048x2048(pkg, gpu_ctx):
+    cfg = _field(pkg, (2048, 2048), "LIKE_NORMAL", 2)
+    _full_metric_checks(pkg, gpu_ctx, cfg, 2)
+
+
+def test_full_size_c5_256cubed(pkg, gpu_ctx):
+    cfg = _field(pkg, (256, 256, 256), "LIKE_POISSON", 1)
+    _full_metric_checks(pkg, gpu_ctx, cfg, 1)
+
+
+def test_full_size_step_properties_1024(pkg, gpu_ctx):
+    """A complete mgvi_step at 1024 x 1024 with 4 residuals: antithetic pairing is exact and the
+    KL estimate decreases; the KL value of the result is reproduced by the oracle."""
+    cfg = _field(pkg, (1024, 1024), "LIKE_NORMAL", 4)
+    m = pkg.model_from_config(cfg, gpu_ctx)
+    res, c = pkg.mgvi_step(m, cfg["data"], 4, cfg["center"], pkg.MGVIConfig(), gpu_ctx, draws=(cfg["Z1"], cfg["Z2"]))
+    S = res.samples
+    assert np.abs(S[:, 0::2] + S[:, 1::2] - 2 * c[:, None]).max() < 1e-12
+    tr = res.info["optimizer_output"]
+    assert tr["f_history"][-1] < tr["f_history"][0]
+    om = oracle_model(cfg)
+    R = 0.5 * (S[:, 0::2] - S[:, 1::2])
+    assert abs(O.mean_neg_log_pstr(om, R, c) - res.mnlp) <= 1e-10 * abs(res.mnlp)
+    m.close()
+
+
+@pytest.mark.parametrize("layout,reference_grid", [(1, True), (2, True), (1, False)])
+def test_polyfit_model(pkg, gpu_ctx, layout, reference_grid):
+    """BASELINE.json configs[0]: the polynomial fit of test/test_models/model_polyfit.jl on the
+    reference's 40-point grids and on the 1000-point C1 grids, 8 residual samples."""
+    from helpers import check_poly_ops
+    cfg = pkg.synthetic.polyfit_config(8, reference_grid=reference_grid, layout=layout)
+    out = check_poly_ops(pkg, gpu_ctx, cfg)
+    for k in ("metric", "fisher", "dense", "kl", "grad", "mean_metric"):
+        assert out[k] < 1e-9, (k, out)
+    assert out["iters_default"][0] == out["iters_default"][1] == [5] * 8
+    assert out["residuals"] < 1e-8, out
+    assert out["cg_step"] < 1e-8 and out["dense_step"] < 1e-9, out
