@@ -91,7 +91,8 @@ def test_default_tolerance_iteration_counts(pkg, gpu_ctx):
     s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(), gpu_ctx)
     R, info = pkg.sample_residuals(s, 4, draws=(cfg["Z1"], cfg["Z2"]), return_info=True)
     Ro, ito, rno = O.sample_residuals_cg(om, cfg["center"], cfg["Z1"], cfg["Z2"])
-    assert np.abs(info["iters"] - ito).max() <= 2, (info["iters"], ito)
+    # ||r|| is not monotone in CG: the first dip below the threshold moves by a few iterations
+    assert np.all(np.abs(info["iters"] - ito) <= 3 + 0.05 * ito), (info["iters"], ito)
     assert rel(R, Ro) < 1e-6          # both stop at ||r|| ~ 1.5e-8 (1 + ||b||)
     s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(abstol=0.0, reltol=0.0, maxiters=9), gpu_ctx)
     R, info = pkg.sample_residuals(s, 4, draws=(cfg["Z1"], cfg["Z2"]), return_info=True)
@@ -114,7 +115,7 @@ def test_many_residuals_lockstep_masking(pkg, gpu_ctx):
     R, info = pkg.sample_residuals(s, 33, draws=(cfg["Z1"], cfg["Z2"]), return_info=True)
     Ro, ito, _ = O.sample_residuals_cg(om, cfg["center"], cfg["Z1"], cfg["Z2"], atol=1e-9, rtol=1e-12)
     assert len(set(info["iters"].tolist())) > 3
-    assert np.abs(info["iters"] - ito).max() <= 2
+    assert np.all(np.abs(info["iters"] - ito) <= 3 + 0.05 * ito)
     for i in range(33):
         assert np.linalg.norm(R[:, i] - Ro[:, i]) <= 1e-8 * np.linalg.norm(Ro[:, i]) + 2e-9, i
     m.close()
