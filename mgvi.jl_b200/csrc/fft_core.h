@@ -73,101 +73,129 @@ SIMT_HD void dft8(double2 (&a)[8]) {
 struct LineView {
     double2* sm;     // base of the unit's buffer (L*n chunks)
     int lgL, l;
-    SIMT_DEVICE double2& at(int k) const { return sm[swz((k << lgL) | l)]; }
+    SIMT_DEVICE int idx(int k) const { return swz((k << lgL) | l); }
+    SIMT_DEVICE double2& at(int k) const { return sm[idx(k)]; }
 };
 
 // Forward FFT of the line whose elements the calling threads hold in v (v[m] = x[lt + m*n/8]).
-// On return the line sits in shared memory in natural order (all threads have passed the final
-// barrier).  EVERY thread of the block must call this (uniform barriers); threads whose unit is
-// out of range pass valid = false and only take part in the barriers.
-// n = 2^log2n >= 8; tw[k] = exp(-2 pi i k / n), k < n.
-SIMT_DEVICE void fft_line_forward(double2 (&v)[8], const LineView& lv, int lt, int log2n,
-                                  const double2* __restrict__ tw, bool valid) {
+// On return v[m] = Z[lt + m*n/8] (each thread keeps its own outputs in registers) AND the whole
+// line sits in shared memory in natural order (all threads have passed the final barrier), so
+// partners can be read.  EVERY thread of the block must call this (uniform barriers); threads
+// whose unit is out of range simply transform zeros inside their own shared buffer (no branches:
+// a branch around each phase costs a register move per live value at every merge point).
+// n = 2^log2n >= 8.  tw is the per-stage twiddle table: for every radix-8 stage with Ns > 1, in
+// stage order, three runs of Ns entries  W^(j), W^(2j), W^(4j)  (j < Ns, W = exp(-2 pi i / (8 Ns))),
+// so that the lanes of a warp (consecutive j) read consecutive 16-byte entries.
+// LG > 0 fixes log2 n at compile time (stage loop unrolled, shifts and swizzle offsets folded
+// into immediates); LG = 0 takes it from log2n_rt.
+template <int LG>
+SIMT_DEVICE void fft_line_forward(double2 (&v)[8], const LineView& lv, int lt, int log2n_rt,
+                                  const double2* __restrict__ tw) {
+    const int log2n = LG ? LG : log2n_rt;
     const int n8 = 1 << (log2n - 3);
+    const int lgL = lv.lgL;
     const int lead = log2n % 3;   // 0: all radix-8; 1: leading radix-2; 2: leading radix-4
-    int lgNs = 0;
+    // linear read-back positions: swz(((lt + m n8) << lgL) | l) = rd0 + m * rd_step once the step is a
+    // multiple of 64 chunks (the swizzle only looks at bits 3..5)
+    const int rd_step = n8 << lgL;
+    const bool rd_fast = (rd_step & 63) == 0;
+    const int rd0 = lv.idx(lt);
     if (lead == 2) {
         // leading radix-4 stage (Ns = 1): two butterflies j = lt + q*n8, inputs v[q + 2t]
-        if (valid) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                dft4(v[q], v[q + 2], v[q + 4], v[q + 6]);
-                const int j4 = (lt + q * n8) << 2;
+        for (int q = 0; q < 2; ++q) {
+            dft4(v[q], v[q + 2], v[q + 4], v[q + 6]);
+            const int j4 = (lt + q * n8) << 2;
 #pragma unroll
-                for (int t = 0; t < 4; ++t) lv.at(j4 + t) = v[q + 2 * t];
-            }
+            for (int t = 0; t < 4; ++t) lv.at(j4 + t) = v[q + 2 * t];
         }
-        lgNs = 2;
     } else if (lead == 1) {
         // leading radix-2 stage (Ns = 1): four butterflies j = lt + q*n8, inputs v[q], v[q + 4]
-        if (valid) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                bfly2(v[q], v[q + 4]);
-                const int j2 = (lt + q * n8) << 1;
-                lv.at(j2) = v[q];
-                lv.at(j2 + 1) = v[q + 4];
-            }
+        for (int q = 0; q < 4; ++q) {
+            bfly2(v[q], v[q + 4]);
+            const int j2 = (lt + q * n8) << 1;
+            lv.at(j2) = v[q];
+            lv.at(j2 + 1) = v[q + 4];
         }
-        lgNs = 1;
     }
     if (lead != 0) {
         SIMT_SYNC();
-        if (valid) {
 #pragma unroll
-            for (int m = 0; m < 8; ++m) v[m] = lv.at(lt + m * n8);
-        }
+        for (int m = 0; m < 8; ++m) v[m] = lv.sm[rd_fast ? rd0 + m * rd_step : lv.idx(lt + m * n8)];
         SIMT_SYNC();
     }
     // radix-8 stages
-    while (true) {
-        if (valid) {
+#pragma unroll
+    for (int lgNs = lead; lgNs < log2n; lgNs += 3) {
+        {
             const int jlo = lt & ((1 << lgNs) - 1);
             if (lgNs > 0) {
-                // twiddles W^(jlo*t), W = exp(-2 pi i / (8 Ns)): three table loads, the rest by products
-                const int jm = jlo << (log2n - 3 - lgNs);
-                const double2 w1 = SIMT_LDG(&tw[jm]);
-                const double2 w2 = SIMT_LDG(&tw[2 * jm]);
-                const double2 w4 = SIMT_LDG(&tw[4 * jm]);
+                // twiddles W^(jlo*t): three coalesced table loads, the other four by products
+                // stage offset: 3 * (sum of the Ns of the earlier radix-8 stages that have twiddles, i.e. Ns > 1)
+                const double2* tws = tw + 3 * (((1 << lgNs) - (1 << lead)) / 7 - (lead == 0 ? 1 : 0)) + jlo;
+                const double2 w1 = SIMT_LDG(tws);
+                const double2 w2 = SIMT_LDG(tws + (1 << lgNs));
                 v[1] = cmul(v[1], w1);
                 v[2] = cmul(v[2], w2);
+                double2 w3 = cmul(w1, w2);
+                v[3] = cmul(v[3], w3);
+                const double2 w4 = SIMT_LDG(tws + (2 << lgNs));
                 v[4] = cmul(v[4], w4);
-                double2 w = cmul(w1, w2);         // W^3
-                v[3] = cmul(v[3], w);
-                w = cmul(w, w4);                  // W^7
-                v[7] = cmul(v[7], w);
-                w = cmul(w1, w4);                 // W^5
-                v[5] = cmul(v[5], w);
-                w = cmul(w2, w4);                 // W^6
-                v[6] = cmul(v[6], w);
+                w3 = cmul(w3, w4);                // W^7
+                v[7] = cmul(v[7], w3);
+                w3 = cmul(w1, w4);                // W^5
+                v[5] = cmul(v[5], w3);
+                w3 = cmul(w2, w4);                // W^6
+                v[6] = cmul(v[6], w3);
             }
             dft8(v);
             const int base = ((lt >> lgNs) << (lgNs + 3)) | jlo;
+            const int cb = (base << lgL) | lv.l;
+            const int sh = lgNs + lgL;
+            if (sh >= 6) {
+                const int w0 = swz(cb);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) lv.at(base + (t << lgNs)) = v[t];
+                for (int t = 0; t < 8; ++t) lv.sm[w0 + (t << sh)] = v[t];
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) lv.sm[swz(cb + (t << sh))] = v[t];
+            }
         }
         SIMT_SYNC();
-        lgNs += 3;
-        if (lgNs >= log2n) break;
-        if (valid) {
+        if (lgNs + 3 < log2n) {
 #pragma unroll
-            for (int m = 0; m < 8; ++m) v[m] = lv.at(lt + m * n8);
+            for (int m = 0; m < 8; ++m) v[m] = lv.sm[rd_fast ? rd0 + m * rd_step : lv.idx(lt + m * n8)];
+            SIMT_SYNC();
         }
-        SIMT_SYNC();
     }
 }
 
-// After fft_line_forward: v[m] <- 2 * ( H(a)[k], H(b)[k] ), k = lt + m*n/8.
+// After fft_line_forward: v[m] <- 2 * ( H(a)[k], H(b)[k] ), k = lt + m*n/8.  Own values come from
+// registers, the partners Z[n-k] from shared memory (they live in thread n/8 - lt, register 7-m).
 // (The factor 2 is folded into the callers' scale constants; powers of two are exact.)
-SIMT_DEVICE void dht_combine_read(double2 (&v)[8], const LineView& lv, int lt, int log2n) {
+template <int LG>
+SIMT_DEVICE void dht_combine_read(double2 (&v)[8], const LineView& lv, int lt, int log2n_rt) {
+    const int log2n = LG ? LG : log2n_rt;
     const int n8 = 1 << (log2n - 3);
-    const int nmask = (1 << log2n) - 1;
+    const int rd_step = n8 << lv.lgL;
+    const bool rd_fast = (rd_step & 63) == 0;
+    const int plt = (n8 - lt) & (n8 - 1);
+    const int p0 = lv.idx(plt);
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int k = lt + m * n8;
-        const double2 zk = lv.at(k);
-        const double2 zn = lv.at((-k) & nmask);
-        v[m] = make_double2(zk.x - zk.y + zn.x + zn.y, zk.x + zk.y + zn.y - zn.x);
+    for (int h = 0; h < 2; ++h) {
+        double2 zn[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = 4 * h + j;
+            const int pm = (lt == 0) ? ((8 - m) & 7) : (7 - m);
+            zn[j] = lv.sm[rd_fast ? p0 + pm * rd_step : lv.idx(plt + pm * n8)];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double2 zk = v[4 * h + j];
+            v[4 * h + j] = make_double2(zk.x - zk.y + zn[j].x + zn[j].y, zk.x + zk.y + zn[j].y - zn[j].x);
+        }
     }
 }
 

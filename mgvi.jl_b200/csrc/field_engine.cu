@@ -41,6 +41,8 @@ struct FieldEngine : Engine {
     long long z1_ld = 0, z1_stride = 1;
     double const_term = 0.0;    // per-point constants of -loglike and of the prior
     int max_L = 4;
+    int prefetch_waves = 1;     // software L2 prefetch distance in resident-block waves (0 = off)
+    bool use_hot = true;        // compile-time-shape kernels for the benchmark sizes
 
     DevBuf A, data, w, q, wbar, center;
     std::map<long long, DevBuf> tw, cas;
@@ -94,6 +96,8 @@ struct FieldEngine : Engine {
         if (N >= (1LL << 31)) fast = false;      // the pass kernels use 32-bit element offsets
         if (const char* e = getenv("MGVIB200_FORCE_GENERIC")) if (atoi(e)) fast = false;
         if (const char* e = getenv("MGVIB200_STRIDED_L")) max_L = std::max(1, atoi(e));
+        if (const char* e = getenv("MGVIB200_PREFETCH_WAVES")) prefetch_waves = std::max(0, atoi(e));
+        if (const char* e = getenv("MGVIB200_NO_HOT")) use_hot = !atoi(e);
         if (!fast)
             for (int i = 0; i < ndim; ++i)
                 if (dims[i] > kNaiveMaxAxis)
@@ -119,14 +123,23 @@ struct FieldEngine : Engine {
             const long long n = dims[i];
             if (fast) {
                 if (tw.count(n)) continue;
-                std::vector<double> t(2 * n);
-                for (long long k = 0; k < n; ++k) {
-                    long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
-                    t[2 * k] = (double)cosl(a);
-                    t[2 * k + 1] = (double)(-sinl(a));
+                // per-stage twiddle runs (fft_core.h): for each radix-8 stage with Ns > 1, W^j, W^2j, W^4j, j < Ns
+                std::vector<double> t;
+                const int lg = ilog2(n), lead = lg % 3;
+                for (int lgNs = lead; lgNs < lg; lgNs += 3) {
+                    if (lgNs == 0) continue;
+                    const long long Ns = 1LL << lgNs;
+                    for (int e = 1; e <= 4; e *= 2)
+                        for (long long j = 0; j < Ns; ++j) {
+                            long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)(e * j) /
+                                            (long double)(8 * Ns);
+                            t.push_back((double)cosl(a));
+                            t.push_back((double)(-sinl(a)));
+                        }
                 }
-                tw[n].ensure(sizeof(double) * 2 * n);
-                rt_h2d(tw[n].p, t.data(), sizeof(double) * 2 * n, ctx->stream);
+                if (t.empty()) { t.push_back(1.0); t.push_back(0.0); }
+                tw[n].ensure(sizeof(double) * t.size());
+                rt_h2d(tw[n].p, t.data(), sizeof(double) * t.size(), ctx->stream);
                 rt_sync(ctx->stream);
             } else {
                 if (cas.count(n)) continue;
@@ -195,6 +208,29 @@ struct FieldEngine : Engine {
         return g;
     }
 
+    // run-time-shape build
+    template <int GEO, int PRO, int EPI, bool DBL>
+    void launch_lg(const FieldPassParams& P, const PassGeo& g, long long grid) {
+        if (g.threads <= 256)
+            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 256, 2, 0, -1, true>, grid, g.threads, g.smem, ctx->stream, P);
+        else if (g.threads <= 512)
+            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 512, 1, 0, -1, true>, grid, g.threads, g.smem, ctx->stream, P);
+        else
+            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 1024, 1, 0, -1, true>, grid, g.threads, g.smem, ctx->stream, P);
+    }
+
+    // compile-time-shape build; the block size follows from (LG, LGL): 2^(LG - 3 + LGL) threads per unit
+    template <int GEO, int PRO, int EPI, bool DBL, int LG, int LGL>
+    void launch_hot(const FieldPassParams& P, const PassGeo& g, long long grid) {
+        constexpr int upt = (LG > 0) ? (1 << (LG - 3 + LGL)) : 256;
+        if (upt <= 256)
+            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 256, MGVI_MINB, LG, LGL, false>, grid, g.threads, g.smem, ctx->stream, P);
+        else if (upt == 512)
+            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 512, 2, LG, LGL, false>, grid, g.threads, g.smem, ctx->stream, P);
+        else
+            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 1024, 1, LG, LGL, false>, grid, g.threads, g.smem, ctx->stream, P);
+    }
+
     template <int GEO, int PRO, int EPI, bool DBL>
     void launch_pass(FieldPassParams P, const PassGeo& g, int nvec, int nsgrp, int nloop) {
         if (g.geo != GEO) throw RtError{"internal: geometry class mismatch", 1};
@@ -209,6 +245,11 @@ struct FieldEngine : Engine {
         } else {
             grid = g.ntb * nsgrp;
         }
+        // prefetch distance: what one wave of resident blocks covers (blocks/SM from the thread count)
+        {
+            const int per_sm = g.threads <= 256 ? MGVI_MINB : (g.threads <= 512 ? 2 : 1);
+            P.prefetch_blocks = (grid > 4LL * ctx->sm_count * per_sm) ? prefetch_waves * ctx->sm_count * per_sm : 0;
+        }
         if (P.fin != FIN_NONE) {
             const size_t np = (P.fin == FIN_TOTAL) ? (size_t)grid : (size_t)nvec * (size_t)g.ntb;
             reduce_ws_ensure(rws, ctx, np, (size_t)std::max(nvec, 1));
@@ -216,12 +257,20 @@ struct FieldEngine : Engine {
             P.counters = rws.counters.as<unsigned>();
         }
         ctx->prof_pre(PRO * 100 + EPI * 10 + (DBL ? 1 : 0));
-        if (g.threads <= 256)
-            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 256, MGVI_MINB>, grid, g.threads, g.smem, ctx->stream, P);
-        else if (g.threads <= 512)
-            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 512, 1>, grid, g.threads, g.smem, ctx->stream, P);
-        else
-            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 1024, 1>, grid, g.threads, g.smem, ctx->stream, P);
+        // The kernels of the CG iteration get fully specialised builds for the benchmark shapes
+        // (2048-point axes: C3; 256-point axes: C5): compile-time length, tile width and no vector loop.
+        constexpr bool hot_c = (GEO == GEO_CONTIG) && !DBL &&
+                               ((PRO == PRO_CG && EPI == EPI_STORE) || (PRO == PRO_LOAD && EPI == EPI_METRIC));
+        constexpr bool hot_s = (GEO == GEO_STRIDED) && (PRO == PRO_LOAD && EPI == EPI_STORE);
+        bool done = false;
+        if (nloop == 1 && use_hot) {
+            if (hot_c && g.log2n == 11) { launch_hot<GEO, PRO, EPI, DBL, hot_c ? 11 : 0, 0>(P, g, grid); done = true; }
+            else if (hot_c && g.log2n == 8) { launch_hot<GEO, PRO, EPI, DBL, hot_c ? 8 : 0, 0>(P, g, grid); done = true; }
+            else if (hot_s && DBL && g.log2n == 11 && g.lgL == 2) { launch_hot<GEO, PRO, EPI, DBL, (hot_s && DBL) ? 11 : 0, 2>(P, g, grid); done = true; }
+            else if (hot_s && DBL && g.log2n == 11 && g.lgL == 1) { launch_hot<GEO, PRO, EPI, DBL, (hot_s && DBL) ? 11 : 0, 1>(P, g, grid); done = true; }
+            else if (hot_s && g.log2n == 8 && g.lgL == 2) { launch_hot<GEO, PRO, EPI, DBL, hot_s ? 8 : 0, 2>(P, g, grid); done = true; }
+        }
+        if (!done) launch_lg<GEO, PRO, EPI, DBL>(P, g, grid);
         ctx->prof_post();
         ctx->launches++;
     }

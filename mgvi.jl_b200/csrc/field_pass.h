@@ -68,6 +68,7 @@ struct FieldPassParams {
     double scale, offset, sigma, inv_sigma2;
     int link, likelihood, first_iter, want_grad;
     int mask_active;                          // skip vectors whose cg.active flag is 0 (CG iterations only)
+    int prefetch_blocks;                      // > 0: hint the inputs of block (this + prefetch_blocks) into L2
     // ---- reduction ------------------------------------------------------------------------
     int fin;
     double* partials; unsigned* counters; double* red_out;
@@ -219,6 +220,67 @@ SIMT_DEVICE void epi_pair(const FieldPassParams& P, int sa, int sb, long long pa
 }
 
 // ------------------------------------------------------------------------------------------
+// Whole-thread versions of the two hot load/store steps of the CG iteration (contiguous and
+// strided geometry, both halves of the pair valid).  The per-element forms above interleave loads
+// with stores to arrays the compiler must assume may alias, which serialises the memory
+// pipeline (and re-reads beta for every element); here every batch issues all its loads first,
+// through __restrict__ pointers, then computes, then stores.
+// ------------------------------------------------------------------------------------------
+template <bool ADJ>
+SIMT_DEVICE void pro_cg_block(double2 (&v)[8], double* __restrict__ p, const double* __restrict__ r,
+                              const double* __restrict__ A, unsigned off_a, unsigned off_b, unsigned step,
+                              long long vec_off, double beta, bool first_iter) {
+    // p = r + beta p (skipped on the first iteration, where p = r already) ; v = A . p
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        double2 pp[4], rr[4], aa[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned oa = off_a + (4 * h + j) * step, ob = off_b + (4 * h + j) * step;
+            pp[j] = ld_pair(p, vec_off + oa, vec_off + ob, true, true, ADJ);
+            aa[j] = ldg_pair(A, oa, ob, true, true, ADJ);
+            if (!first_iter) rr[j] = ld_pair(r, vec_off + oa, vec_off + ob, true, true, ADJ);
+        }
+        if (!first_iter) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned oa = off_a + (4 * h + j) * step, ob = off_b + (4 * h + j) * step;
+                pp[j] = make_double2(rr[j].x + beta * pp[j].x, rr[j].y + beta * pp[j].y);
+                st_pair(p, vec_off + oa, vec_off + ob, true, true, ADJ, pp[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[4 * h + j] = make_double2(aa[j].x * pp[j].x, aa[j].y * pp[j].y);
+    }
+}
+
+template <bool ADJ>
+SIMT_DEVICE void epi_metric_block(const double2 (&v)[8], double* __restrict__ out, const double* __restrict__ vin,
+                                  const double* __restrict__ A, unsigned off_a, unsigned off_b, unsigned step,
+                                  long long out_off, long long vin_off, double scale, double& acc) {
+    // out = vin + scale * A . val ; acc += vin . out
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        double2 vi[4], aa[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned oa = off_a + (4 * h + j) * step, ob = off_b + (4 * h + j) * step;
+            vi[j] = ld_pair(vin, vin_off + oa, vin_off + ob, true, true, ADJ);
+            aa[j] = ld_pair(A, oa, ob, true, true, ADJ);       // plain load: must not be hoisted above the transform
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned oa = off_a + (4 * h + j) * step, ob = off_b + (4 * h + j) * step;
+            const double2 val = v[4 * h + j];
+            const double2 o = make_double2(vi[j].x + scale * (aa[j].x * val.x), vi[j].y + scale * (aa[j].y * val.y));
+            st_pair(out, out_off + oa, out_off + ob, true, true, ADJ, o);
+            acc += vi[j].x * o.x;
+            acc += vi[j].y * o.y;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // reductions
 // ------------------------------------------------------------------------------------------
 // Sum `v` over segments of `seg` consecutive threads (seg a power of two dividing the block size,
@@ -336,9 +398,12 @@ SIMT_HD long long field_pass_smem_bytes(int n, int L, int G) {
 //   GEO_PAIRVEC: 1-D fields; a unit = two vectors
 // All sizes are powers of two, so thread/unit decoding is shifts and masks.  Element offsets
 // inside a vector are 32-bit (N < 2^31, checked on the host).
-template <int GEO, int PRO, int EPI, bool DOUBLE>
+// LG > 0 / LGL >= 0 fix log2(n) / log2(L) at compile time; LOOP = false drops the loop over vectors
+// (nloop == 1): with everything known the shared-memory swizzle offsets fold into immediates and
+// nothing loop-invariant is left for the compiler to hoist and spill.
+template <int GEO, int PRO, int EPI, bool DOUBLE, int LG, int LGL, bool LOOP>
 SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_raw) {
-    const int log2n = P.log2n, lgL = P.lgL;
+    const int log2n = LG ? LG : P.log2n, lgL = (LGL >= 0) ? LGL : P.lgL;
     const int n8 = 1 << (log2n - 3);
     const int tid = SIMT_TID;
     const int lg_upt = log2n - 3 + lgL;          // threads per unit = 2^lg_upt
@@ -361,6 +426,38 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
     const bool use_active = (P.mask_active != 0);
     if (use_active && !pairvec && P.nloop == 1) {
         if (!P.cg.active[sgrp]) return;    // uniform for the whole block
+    }
+
+    // Software prefetch: blocks are dispatched in index order, so the block `prefetch_blocks` ahead
+    // starts about one residency later; pulling its per-sample input rows into L2 now takes the DRAM
+    // latency off that block's load phase (the shared operands A and w stay in L2 by themselves).
+    if (!pairvec && P.prefetch_blocks > 0 && P.nloop == 1) {
+        const long long b2 = SIMT_BID + P.prefetch_blocks;
+        if (b2 < SIMT_NBID) {
+            const long long bt2 = b2 / P.nsgrp;
+            const long long s2 = b2 - bt2 * P.nsgrp;
+            const long long u2 = bt2 * P.G + g;
+            if (u2 < P.units_per_vec) {
+                if (GEO == GEO_CONTIG) {
+                    // a row pair is one contiguous chunk of 2n doubles
+                    const long long o2 = s2 * P.N + ((2 * u2) << log2n);
+                    const unsigned bytes = 16u << log2n;
+                    if (tu == 0) {
+                        if (PRO == PRO_CG) { SIMT_PREFETCH_BULK_L2(P.p + o2, bytes); if (!P.first_iter) SIMT_PREFETCH_BULK_L2(P.r + o2, bytes); }
+                        if (PRO == PRO_LOAD || PRO == PRO_AMP) SIMT_PREFETCH_BULK_L2(P.in + s2 * P.in_ld + ((2 * u2) << log2n), bytes);
+                        if (EPI == EPI_METRIC) SIMT_PREFETCH_BULK_L2(P.vin + s2 * P.vin_ld + ((2 * u2) << log2n), bytes);
+                    }
+                } else if (PRO == PRO_LOAD) {
+                    const long long o2 = u2 >> P.lg_tpo, cb2 = u2 & ((1LL << P.lg_tpo) - 1);
+                    const double* q = P.in + s2 * P.in_ld + ((o2 << log2n) + lt) * P.inner + (cb2 << (lgL + 1)) + 2 * l;
+                    // one hint per row segment (the L = 2^lgL lanes of a row share a line)
+                    if (l == 0) {
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) SIMT_PREFETCH_L2(q + (long long)m * n8 * P.inner);
+                    }
+                }
+            }
+        }
     }
 
     double acc_a = 0.0, acc_b = 0.0;
@@ -390,13 +487,14 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
     }
     int sa = 0, sb = 0;
     bool va = false, vb = false;
-    for (int it = 0; it < P.nloop; ++it) {
+    const int nloop = LOOP ? P.nloop : 1;
+    for (int it = 0; it < nloop; ++it) {
         if (pairvec) {
-            const long long pair = (bt * P.nloop + it) * P.G + g;
+            const long long pair = (bt * nloop + it) * P.G + g;
             sa = (int)(2 * pair); sb = sa + 1;
             va = sa < P.nvec; vb = sb < P.nvec;
         } else {
-            sa = sb = sgrp * P.nloop + it;
+            sa = sb = sgrp * nloop + it;
             va = vb = unit_ok && sa < P.nvec;
         }
         if (use_active) {
@@ -405,30 +503,66 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
         }
         const bool valid = va || vb;
         double2 v[8];
-        if (valid) {
+        if (pairvec) {
+            // the two halves of a pair are different vectors: per-half predicates
 #pragma unroll
             for (int m = 0; m < 8; ++m)
-                v[m] = pro_pair<PRO>(P, sa, sb, off_a + m * step, off_b + m * step, va, vb, adj, acc_a, acc_b);
+                v[m] = valid ? pro_pair<PRO>(P, sa, sb, off_a + m * step, off_b + m * step, va, vb, false, acc_a, acc_b)
+                             : make_double2(0.0, 0.0);
+        } else if (valid) {
+            if (PRO == PRO_CG) {
+                pro_cg_block<GEO == GEO_STRIDED>(v, P.p, P.r, P.A, off_a, off_b, step, (long long)sa * P.N,
+                                                 P.first_iter ? 0.0 : P.cg.beta[sa], P.first_iter != 0);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; ++m)
+                    v[m] = pro_pair<PRO>(P, sa, sb, off_a + m * step, off_b + m * step, true, true, adj, acc_a, acc_b);
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < 8; ++m) v[m] = make_double2(0.0, 0.0);
         }
         if (it > 0) SIMT_SYNC();   // previous iteration's combine reads vs this iteration's writes
-        fft_line_forward(v, lv, lt, log2n, P.tw, valid);
-        if (valid) dht_combine_read(v, lv, lt, log2n);
+        fft_line_forward<LG>(v, lv, lt, log2n, P.tw);
+        dht_combine_read<LG>(v, lv, lt, log2n);
+        SIMT_OPAQUE_U32(off_a); SIMT_OPAQUE_U32(off_b); SIMT_OPAQUE_U32(step);
         if (DOUBLE) {
             if (valid) {
 #pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    double2 wv = ldg_pair(P.w, off_a + m * step, off_b + m * step, va, vb, adj);
-                    v[m] = make_double2(v[m].x * wv.x, v[m].y * wv.y);
+                for (int h = 0; h < 2; ++h) {
+                    double2 wv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int m = 4 * h + j;
+                        // plain (coherent) loads on purpose: read-only-path loads may be hoisted above the
+                        // barriers to the top of the kernel, which keeps 32 registers live through the
+                        // whole first transform and spills
+                        wv[j] = pairvec ? ld_pair(P.w, off_a + m * step, off_b + m * step, va, vb, false)
+                                        : ld_pair(P.w, off_a + m * step, off_b + m * step, true, true, adj);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        v[4 * h + j] = make_double2(v[4 * h + j].x * wv[j].x, v[4 * h + j].y * wv[j].y);
                 }
             }
             SIMT_SYNC();
-            fft_line_forward(v, lv, lt, log2n, P.tw, valid);
-            if (valid) dht_combine_read(v, lv, lt, log2n);
+            fft_line_forward<LG>(v, lv, lt, log2n, P.tw);
+            dht_combine_read<LG>(v, lv, lt, log2n);
+            SIMT_OPAQUE_U32(off_a); SIMT_OPAQUE_U32(off_b); SIMT_OPAQUE_U32(step);
         }
         if (valid) {
+            if (pairvec) {
 #pragma unroll
-            for (int m = 0; m < 8; ++m)
-                epi_pair<EPI>(P, sa, sb, off_a + m * step, off_b + m * step, va, vb, adj, v[m], acc_a, acc_b, accv[m]);
+                for (int m = 0; m < 8; ++m)
+                    epi_pair<EPI>(P, sa, sb, off_a + m * step, off_b + m * step, va, vb, false, v[m], acc_a, acc_b, accv[m]);
+            } else if (EPI == EPI_METRIC) {
+                epi_metric_block<GEO == GEO_STRIDED>(v, P.out, P.vin, P.A, off_a, off_b, step, (long long)sa * P.out_ld,
+                                                     (long long)sa * P.vin_ld, P.scale, acc_a);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; ++m)
+                    epi_pair<EPI>(P, sa, sb, off_a + m * step, off_b + m * step, true, true, adj, v[m], acc_a, acc_b, accv[m]);
+            }
         }
     }
     // ---- accumulated per-element outputs ---------------------------------------------------

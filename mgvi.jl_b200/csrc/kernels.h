@@ -21,10 +21,12 @@ namespace mgvi {
 #endif
 
 // MAXT = 256: up to 256 threads, MINB resident blocks per SM wanted; MAXT = 1024: wide tiles.
-template <int GEO, int PRO, int EPI, bool DOUBLE, int MAXT, int MINB>
+// LG > 0 / LGL >= 0: log2 of the transform length / of the tile width fixed at compile time (hot
+// sizes), LOOP = false: one vector per block; LG = 0, LGL = -1, LOOP = true: everything at run time.
+template <int GEO, int PRO, int EPI, bool DOUBLE, int MAXT, int MINB, int LG, int LGL, bool LOOP>
 SIMT_GLOBAL2(MAXT, MINB) k_field_pass(SIMT_KARGS(FieldPassParams)) {
     SIMT_SMEM_DECL
-    field_pass_body<GEO, PRO, EPI, DOUBLE>(P, simt_smem);
+    field_pass_body<GEO, PRO, EPI, DOUBLE, LG, LGL, LOOP>(P, simt_smem);
 }
 
 template <int PRO>

@@ -26,6 +26,13 @@
 #define SIMT_ATOMIC_ADD_I32(p, v) atomicAdd((p), (v))
 #define SIMT_LDG(p) __ldg(p)
 #define SIMT_LDCG(p) __ldcg(p)
+// L2 prefetch hints (no register, no scoreboard): one contiguous chunk / one line
+#define SIMT_PREFETCH_BULK_L2(ptr, bytes)                                                          \
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"((unsigned)(bytes)) : "memory")
+#define SIMT_PREFETCH_L2(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))
+// optimisation fence on a 32-bit value: stops the compiler from precomputing (and spilling) the
+// addresses of a later phase at the top of the kernel
+#define SIMT_OPAQUE_U32(x) asm volatile("" : "+r"(x))
 #define SIMT_KERNEL(name, params_t, body_call)                                   \
     __global__ void name(const params_t P) {                                     \
         extern __shared__ __align__(16) unsigned char simt_smem[];               \
@@ -50,6 +57,9 @@
 #define SIMT_ATOMIC_ADD_I32(p, v) simt_emu::atomic_add_i32((p), (v))
 #define SIMT_LDG(p) (*(p))
 #define SIMT_LDCG(p) (*(p))
+#define SIMT_PREFETCH_BULK_L2(ptr, bytes) ((void)0)
+#define SIMT_PREFETCH_L2(ptr) ((void)0)
+#define SIMT_OPAQUE_U32(x) ((void)0)
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }

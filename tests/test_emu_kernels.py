@@ -39,12 +39,14 @@ def test_metric_1d_all_radix_leads(pkg, emu_ctx, n):
     ((8, 64), "LIKE_POISSON", None),
     ((32, 8), "LIKE_NORMAL", 1),        # blocked [mu; var] layout
     ((8, 16, 8), "LIKE_POISSON", None),
+    ((8, 256), "LIKE_POISSON", None),   # 256-point rows: compile-time-length kernels (contiguous)
+    ((256, 8), "LIKE_NORMAL", 0),       # 256-point columns: compile-time-length kernels (strided, fused)
     ((40,), "LIKE_NORMAL", 2),          # the reference fixture's length: generic (non power of two) path
     ((6, 10), "LIKE_POISSON", None),
 ])
 def test_field_ops_vs_oracle(pkg, emu_ctx, dims, like, layout):
     cfg = _field(pkg, dims, like, 3 if len(dims) == 1 else 2, layout)
-    assert_field_ops(check_field_ops(pkg, emu_ctx, cfg, check_step=True))
+    assert_field_ops(check_field_ops(pkg, emu_ctx, cfg, check_step=True), cfg)
 
 
 def test_identity_link_and_normal(pkg, emu_ctx):

@@ -1,0 +1,83 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tools/multigpu_check.py
+
+Residual samples are sharded by contiguous column blocks; every rank runs the
+full mgvi_step on its shard with NCCL all-reduces of the KL value / gradient input / mean metric
+weight inside the library.  Rank 0 also runs the same step unsharded on one GPU and through the
+CPU oracle; all three must agree."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as g  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = g.load_package()
+    syn = pkg.synthetic
+    ok = True
+    for dims, like, n in [((256, 256), syn.LIKE_NORMAL, 8), ((4096,), syn.LIKE_POISSON, 8), ((32, 32, 32), syn.LIKE_POISSON, 8)]:
+        cfg = syn.field_config(dims, like, n, field_std=0.5)
+        ctx = pkg.MGVIContext(device=local)
+        box = [ctx.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.init_comm(rank, world, box[0])
+        model = pkg.model_from_config(cfg, ctx)
+        nl = n // world
+        sl = slice(rank * nl, (rank + 1) * nl)
+        Z1, Z2 = np.asfortranarray(cfg["Z1"][:, sl]), np.asfortranarray(cfg["Z2"][:, sl])
+        conf = pkg.MGVIConfig(linsolver=pkg.B200CG(abstol=0.0, reltol=1e-12))
+        res, center = pkg.mgvi_step(model, cfg["data"], nl, cfg["center"], conf, ctx, draws=(Z1, Z2))
+        # sharded KL value/gradient (all-reduced inside) must be identical on every rank
+        f, grad = pkg.kl_value_grad(model, cfg["center"], 0.5 * (res.samples[:, 0::2] - res.samples[:, 1::2]))
+        t = torch.tensor([f, float(np.abs(grad).sum()), res.mnlp, float(np.abs(center).sum())], dtype=torch.float64,
+                         device="cuda")
+        tmax, tmin = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        same = bool(torch.all(tmax == tmin))
+        # gather the sharded samples in canonical column order on rank 0
+        S_local = torch.from_numpy(np.ascontiguousarray(res.samples.T)).cuda()
+        parts = [torch.empty_like(S_local) for _ in range(world)]
+        dist.all_gather(parts, S_local)
+        S = torch.cat(parts, dim=0).cpu().numpy().T
+        if rank == 0:
+            import oracle as O
+            from helpers import TIGHT_O, oracle_model, rel
+            ctx1 = pkg.MGVIContext(device=local)
+            m1 = pkg.model_from_config(cfg, ctx1)
+            res1, c1 = pkg.mgvi_step(m1, cfg["data"], n, cfg["center"], conf, ctx1, draws=(cfg["Z1"], cfg["Z2"]))
+            ref = O.mgvi_step(oracle_model(cfg), cfg["center"], Z1=cfg["Z1"], Z2=cfg["Z2"], **TIGHT_O)
+            e1, e2 = rel(center, c1), rel(S, res1.samples)
+            e3, e4 = rel(center, ref["center"]), rel(S, ref["samples"])
+            tr, tr1 = res.info["optimizer_output"], res1.info["optimizer_output"]
+            good = same and e1 < 1e-10 and e2 < 1e-10 and e3 < 1e-9 and e4 < 1e-9 and tr["cg_updates"] == tr1["cg_updates"]
+            ok = ok and good
+            print("dims %s world %d: ranks identical %s | vs 1-GPU center %.2e samples %.2e | vs oracle center %.2e "
+                  "samples %.2e | traces %s %s -> %s" % (dims, world, same, e1, e2, e3, e4, tr["cg_updates"],
+                                                        tr1["cg_updates"], "PASS" if good else "FAIL"), flush=True)
+            m1.close(); ctx1.close()
+        model.close()
+    flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    if flag.item() != 1.0:
+        sys.exit(1)
+    if rank == 0:
+        print("MULTIGPU CHECK PASS")
+
+
+if __name__ == "__main__":
+    main()
