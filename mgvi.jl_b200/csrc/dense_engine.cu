@@ -1,7 +1,388 @@
-// Dense-linear engine (BASELINE.json configs[3]) -- placeholder until implemented.
+// Dense-linear engine -- BASELINE.json configs[3]: mu = J xi with a dense (m x k) Jacobian,
+// Normal(mu, sigma) data; the `DenseMatrix` operator type `_get_operator_type(::MatrixInversion)`
+// selects (src/residual_samplers.jl:56) and the FullJacobianFunc / FullResidualSampler pair of
+// BASELINE.json's north_star.
+//
+//   M = J' F J + I  (F = 1/sigma^2)            FP64 tensor-core rank-k update (dmma_gemm.h)
+//   MatrixInversion sampler (src/residual_samplers.jl:95-123): the reference forms inv(M) and its
+//   lower Cholesky factor L_Sigma; here (restated for an upper factor):
+//       Mf = P M P (index reversal) = R' R  (blocked upper Cholesky, trailing updates on DMMA)
+//       L_Sigma = P R^-1 P   (lower, L_Sigma L_Sigma' = M^-1),   residuals = P R^-1 (P Z)
+//   no explicit inverse of M is formed.
+//   CG sampler and Newton phase work on M directly (k x k GEMM per iteration).
+//   KL value / gradient use the quadratic form of the Normal-linear model:
+//       -loglike(p) = 1/2 d'd/sigma^2 - p'h + 1/2 p'G p,  h = J'd/sigma^2,  G = M - I
+#include <algorithm>
 #include "engine.h"
+#include "kernels.h"
+#include "dmma_gemm.h"
+
 namespace mgvi {
-Engine* make_dense_engine(mgvib200_ctx*, const mgvib200_model_desc&) {
-    throw RtError{"DENSE_LINEAR model: not implemented yet", MGVIB200_ERR_UNSUPPORTED};
+
+static const int kNb = 64;     // Cholesky / triangular-solve block size
+
+SIMT_GLOBAL2(256, 1) k_dmma_gemm(SIMT_KARGS(GemmParams)) { SIMT_SMEM_DECL gemm_body(P, simt_smem); }
+
+struct TriParams {
+    double* A; long long ld;      // matrix holding the nb x nb diagonal block at (j0, j0)
+    double* X; long long ldx;     // right-hand sides / panel
+    int j0, nb, ncols, c0, mode, n;
+};
+enum { TRI_POTRF = 0, TRI_PANEL = 1, TRI_BACK = 2, TRI_SYM = 3, TRI_EYE = 4 };
+
+// TRI_POTRF: upper Cholesky of the diagonal block in place (one block).
+// TRI_PANEL: X = R_jj^-T A_panel for columns c0.. of block row j0 (thread per column), in place.
+// TRI_BACK : Y = R_jj^-1 W for rows j0..j0+nb of X (thread per column), in place.
+// TRI_SYM  : mirror the upper triangle into the lower one.   TRI_EYE: A = identity.
+SIMT_DEVICE void tri_body(const TriParams& P, unsigned char* smem) {
+    double* S = reinterpret_cast<double*>(smem);          // [nb][nb + 1]
+    const int nb = P.nb, lds = nb + 1, tid = SIMT_TID, nt = SIMT_NTID;
+    if (P.mode == TRI_SYM || P.mode == TRI_EYE) {
+        const long long total = (long long)P.n * P.n;
+        for (long long idx = SIMT_BID * nt + tid; idx < total; idx += SIMT_NBID * nt) {
+            const long long r = idx % P.n, c = idx / P.n;
+            if (P.mode == TRI_EYE) P.A[r + c * P.ld] = (r == c) ? 1.0 : 0.0;
+            else if (r > c) P.A[r + c * P.ld] = P.A[c + r * P.ld];
+        }
+        return;
+    }
+    // diagonal block -> shared (S[row][col])
+    for (int idx = tid; idx < nb * nb; idx += nt) {
+        const int r = idx % nb, c = idx / nb;
+        S[r * lds + c] = P.A[(P.j0 + r) + (long long)(P.j0 + c) * P.ld];
+    }
+    SIMT_SYNC();
+    if (P.mode == TRI_POTRF) {
+        for (int j = 0; j < nb; ++j) {
+            if (tid == 0) S[j * lds + j] = sqrt(S[j * lds + j]);
+            SIMT_SYNC();
+            const double d = S[j * lds + j];
+            for (int c = j + 1 + tid; c < nb; c += nt) S[j * lds + c] /= d;
+            SIMT_SYNC();
+            // trailing update of the upper triangle: S[a][b] -= R[j][a] R[j][b], j < a <= b
+            const int rem = nb - j - 1;
+            for (int idx = tid; idx < rem * rem; idx += nt) {
+                const int a = j + 1 + idx / rem, b = j + 1 + idx % rem;
+                if (a <= b) S[a * lds + b] -= S[j * lds + a] * S[j * lds + b];
+            }
+            SIMT_SYNC();
+        }
+        for (int idx = tid; idx < nb * nb; idx += nt) {
+            const int r = idx % nb, c = idx / nb;
+            P.A[(P.j0 + r) + (long long)(P.j0 + c) * P.ld] = (r <= c) ? S[r * lds + c] : 0.0;
+        }
+        return;
+    }
+    // column tile -> shared T[i][tid] (after S)
+    double* T = S + nb * lds;
+    const int ncol_blk = nt;
+    const long long cbase = P.c0 + SIMT_BID * ncol_blk;
+    for (int idx = tid; idx < nb * ncol_blk; idx += nt) {
+        const int i = idx % nb, c = idx / nb;
+        if (cbase + c < P.c0 + P.ncols) T[i * ncol_blk + c] = P.X[(P.j0 + i) + (cbase + c) * P.ldx];
+    }
+    SIMT_SYNC();
+    if (cbase + tid < P.c0 + P.ncols) {
+        if (P.mode == TRI_PANEL) {
+            // solve R_jj' x = a : x_i = (a_i - sum_{l<i} R[l][i] x_l) / R[i][i]
+            for (int i = 0; i < nb; ++i) {
+                double acc = T[i * ncol_blk + tid];
+                for (int l = 0; l < i; ++l) acc -= S[l * lds + i] * T[l * ncol_blk + tid];
+                T[i * ncol_blk + tid] = acc / S[i * lds + i];
+            }
+        } else {
+            // solve R_jj y = w : y_i = (w_i - sum_{l>i} R[i][l] y_l) / R[i][i]
+            for (int i = nb - 1; i >= 0; --i) {
+                double acc = T[i * ncol_blk + tid];
+                for (int l = i + 1; l < nb; ++l) acc -= S[i * lds + l] * T[l * ncol_blk + tid];
+                T[i * ncol_blk + tid] = acc / S[i * lds + i];
+            }
+        }
+    }
+    SIMT_SYNC();
+    for (int idx = tid; idx < nb * ncol_blk; idx += nt) {
+        const int i = idx % nb, c = idx / nb;
+        if (cbase + c < P.c0 + P.ncols) P.X[(P.j0 + i) + (cbase + c) * P.ldx] = T[i * ncol_blk + c];
+    }
 }
+
+SIMT_GLOBAL(128) k_tri(SIMT_KARGS(TriParams)) { SIMT_SMEM_DECL tri_body(P, simt_smem); }
+
+namespace {
+
+struct DenseEngine : Engine {
+    long long m = 0, k = 0;
+    double sigma = 1.0, inv_s2 = 1.0, dd = 0.0, const_term = 0.0;
+    int layout = 0;
+    long long z1_stride = 1;
+    DevBuf J, data, M, h, center, Mf, W, P2, MP, gsum, ws_r, ws_p, ws_t, n_x, n_r, n_p, n_t, Rinv;
+    ReduceWs rws;
+    CgWs cgws, ncgws;
+    CgScalars ncg_sc;
+    bool ncg_first = true, have_chol = false;
+    int h_act = 0;
+
+    ~DenseEngine() override {
+        DevBuf* all[] = {&J, &data, &M, &h, &center, &Mf, &W, &P2, &MP, &gsum, &ws_r, &ws_p, &ws_t, &n_x, &n_r, &n_p,
+                         &n_t, &Rinv, &rws.partials, &rws.counters, &rws.red};
+        for (auto* b : all) b->release();
+    }
+
+    void gemm(const double* A, long long a_row, long long a_k, const double* B, long long b_k, long long b_col,
+              double* C, long long ldc, int Mr, int Nc, int Kr, double alpha, double beta, bool upper_only = false) {
+        if (Mr <= 0 || Nc <= 0) return;
+        GemmParams g;
+        g.A = A; g.a_row = a_row; g.a_k = a_k; g.B = B; g.b_k = b_k; g.b_col = b_col; g.C = C; g.ldc = ldc;
+        g.M = Mr; g.N = Nc; g.K = Kr; g.alpha = alpha; g.beta = beta; g.upper_only = upper_only ? 1 : 0;
+        g.ntm = (Mr + kGemmBM - 1) / kGemmBM; g.ntn = (Nc + kGemmBN - 1) / kGemmBN;
+        ctx->prof_pre(3000 + (upper_only ? 1 : 0));
+        rt_launch(k_dmma_gemm, (long long)g.ntm * g.ntn, 256, sizeof(double) * 2 * kGemmBM * kGemmLd, ctx->stream, g);
+        ctx->prof_post();
+        ctx->launches++;
+    }
+
+    void tri(int mode, double* A, long long ld, double* X, long long ldx, int j0, int nb, int c0, int ncols, int n) {
+        TriParams t;
+        t.A = A; t.ld = ld; t.X = X; t.ldx = ldx; t.j0 = j0; t.nb = nb; t.c0 = c0; t.ncols = ncols; t.mode = mode; t.n = n;
+        long long grid = 1;
+        if (mode == TRI_PANEL || mode == TRI_BACK) grid = (ncols + 127) / 128;
+        if (mode == TRI_SYM || mode == TRI_EYE) grid = std::min<long long>(((long long)n * n + 127) / 128, 4096);
+        if ((mode == TRI_PANEL || mode == TRI_BACK) && ncols <= 0) return;
+        const size_t smem = sizeof(double) * ((size_t)nb * (nb + 1) + (size_t)nb * 128);
+        ctx->prof_pre(3100 + mode);
+        rt_launch(k_tri, grid, 128, smem, ctx->stream, t);
+        ctx->prof_post();
+        ctx->launches++;
+    }
+
+    VecParams vp() const {
+        VecParams P;
+        memset(&P, 0, sizeof P);
+        P.nvec = 1; P.N = k;
+        return P;
+    }
+
+    void setup(const mgvib200_model_desc& d) {
+        m = d.m; k = d.k; sigma = d.sigma; layout = d.lambda_layout;
+        if (d.likelihood != MGVIB200_LIKE_NORMAL) throw RtError{"DENSE_LINEAR: Normal likelihood only", 1};
+        if (!d.J || !d.data || m < 1 || k < 1 || d.n_data != m) throw RtError{"DENSE_LINEAR: J (m x k) and m data values are required", 1};
+        if (!(sigma > 0)) throw RtError{"DENSE_LINEAR: sigma must be positive", 1};
+        if (ctx->world > 1) throw RtError{"DENSE_LINEAR: replicas only (SURVEY.md 8e); run one replica per GPU", 3};
+        inv_s2 = (1.0 / sigma) * (1.0 / sigma);
+        n_theta = k;
+        n_lambda = (layout == MGVIB200_LAYOUT_MU_ONLY) ? m : 2 * m;
+        z1_stride = (layout == MGVIB200_LAYOUT_INTERLEAVED) ? 2 : 1;
+        J.ensure(8 * m * k); data.ensure(8 * m); M.ensure(8 * k * k); h.ensure(8 * k); center.ensure(8 * k);
+        rt_h2d(J.p, d.J, 8 * m * k, ctx->stream);
+        rt_h2d(data.p, d.data, 8 * m, ctx->stream);
+        dd = 0.0;
+        for (long long i = 0; i < m; ++i) dd += d.data[i] * d.data[i];
+        dd *= inv_s2;
+        const_term = (double)m * (log(sigma) + 0.5 * log(2.0 * M_PI)) + 0.5 * (double)k * log(2.0 * M_PI);
+        // M = I + J'J / sigma^2 : identity, rank-m update of the upper block tiles on DMMA, mirror
+        tri(TRI_EYE, M.as<double>(), k, nullptr, 0, 0, kNb, 0, 0, (int)k);
+        gemm(J.as<double>(), m, 1, J.as<double>(), 1, m, M.as<double>(), k, (int)k, (int)k, (int)m, inv_s2, 1.0, true);
+        tri(TRI_SYM, M.as<double>(), k, nullptr, 0, 0, kNb, 0, 0, (int)k);
+        // h = J'd / sigma^2
+        gemm(J.as<double>(), m, 1, data.as<double>(), 1, m, h.as<double>(), k, (int)k, 1, (int)m, inv_s2, 0.0);
+        rt_sync(ctx->stream);
+    }
+
+    void linearize(const double* x) override { rt_d2d(center.p, x, 8 * k, ctx->stream); }
+
+    void get_weights(double* w_host, double* q_host) override {
+        for (long long i = 0; i < m; ++i) {
+            if (w_host) w_host[i] = inv_s2;
+            if (q_host) q_host[i] = 1.0 / sigma;
+        }
+    }
+
+    void apply_M(const double* V, int nv, double* out) {
+        // M symmetric: out[a, v] = sum_i M[i + a k] V[i + v k]
+        gemm(M.as<double>(), k, 1, V, 1, k, out, k, (int)k, nv, (int)k, 1.0, 0.0);
+    }
+
+    void metric_apply(const double* V, int64_t nv, double* MV) override { apply_M(V, (int)nv, MV); }
+
+    void sample_cg(const double* Z1, const double* Z2, int64_t n, const mgvib200_cg_opts& o, double* R,
+                   int64_t* iters_host, double* rnorm_host) override {
+        const int nvec = (int)n;
+        const size_t vb = 8 * (size_t)k * nvec;
+        ws_r.ensure(vb); ws_p.ensure(vb); ws_t.ensure(vb);
+        cgws.ensure(nvec);
+        const long long itmax = o.maxiters > 0 ? o.maxiters : k;
+        CgScalars sc = cgws.scalars(o.abstol, o.reltol, itmax, CG_KRYLOV);
+        rt_memset(cgws.n_active.p, 0, sizeof(int) * 4, ctx->stream);
+        rt_event_record(ctx->ev0, ctx->stream);
+        // b = J'(sqrt(F) n1) + eta   (src/residual_samplers.jl:77): t = eta, t += (1/sigma) J' n1_mu
+        rt_d2d(ws_t.p, Z2, vb, ctx->stream);
+        gemm(J.as<double>(), m, 1, Z1, z1_stride, n_lambda, ws_t.as<double>(), k, (int)k, nvec, (int)m, 1.0 / sigma, 1.0);
+        vec_cg_init(ctx, rws, sc, ws_t.as<double>(), k, R, ws_r.as<double>(), ws_p.as<double>(), k, nvec);
+        int* hp = ctx->h_pinned;
+        rt_d2h(hp, cgws.n_active.p, sizeof(int), ctx->stream);
+        rt_sync(ctx->stream);
+        long long it = 0;
+        int poll = 1;
+        while (hp[0] > 0 && it < itmax) {
+            for (int q = 0; q < poll && it < itmax; ++q, ++it) {
+                if (it > 0) {
+                    VecParams P = vp();
+                    P.op = VOP_CG_PUPD; P.nvec = nvec; P.r = ws_r.as<double>(); P.p = ws_p.as<double>(); P.cg = sc;
+                    vec_launch(ctx, rws, P);
+                }
+                apply_M(ws_p.as<double>(), nvec, ws_t.as<double>());
+                {
+                    VecParams P = vp();
+                    P.op = VOP_CG_PAP; P.nvec = nvec; P.p = ws_p.as<double>(); P.Ap = ws_t.as<double>(); P.cg = sc;
+                    P.fin = FIN_CG_PAP;
+                    vec_launch(ctx, rws, P);
+                }
+                vec_cg_update(ctx, rws, sc, R, ws_r.as<double>(), ws_p.as<double>(), ws_t.as<double>(), k, nvec);
+            }
+            rt_d2h(hp, cgws.n_active.p, sizeof(int), ctx->stream);
+            rt_sync(ctx->stream);
+            if (poll < 8) poll *= 2;
+        }
+        rt_event_record(ctx->ev1, ctx->stream);
+        std::vector<int> hi(nvec);
+        std::vector<double> hr(nvec);
+        rt_d2h(hi.data(), cgws.iters.p, sizeof(int) * nvec, ctx->stream);
+        rt_d2h(hr.data(), cgws.rnorm.p, 8 * nvec, ctx->stream);
+        rt_sync(ctx->stream);
+        ctx->sampler_ms = rt_event_ms(ctx->ev0, ctx->ev1);
+        long long mx = 0;
+        for (int i = 0; i < nvec; ++i) {
+            if (iters_host) iters_host[i] = hi[i];
+            if (rnorm_host) rnorm_host[i] = hr[i];
+            mx = std::max<long long>(mx, hi[i]);
+        }
+        ctx->lockstep_iters = mx;
+    }
+
+    // Mf = P M P = R'R, R upper, blocked right-looking; the factor stays in Mf (upper triangle)
+    void factorize() {
+        if (have_chol) return;
+        Mf.ensure(8 * k * k);
+        // flip rows and columns: Mf[i][j] = M[k-1-i][k-1-j]; with M symmetric a flip of the flat array does it
+        VecParams P = vp();
+        P.op = VOP_FLIP; P.N = k * k; P.in = M.as<double>(); P.out = Mf.as<double>();
+        vec_launch(ctx, rws, P);
+        double* A = Mf.as<double>();
+        for (long long j0 = 0; j0 < k; j0 += kNb) {
+            const int nb = (int)std::min<long long>(kNb, k - j0);
+            tri(TRI_POTRF, A, k, nullptr, 0, (int)j0, nb, 0, 0, (int)k);
+            const int rest = (int)(k - j0 - nb);
+            if (rest > 0) {
+                tri(TRI_PANEL, A, k, A, k, (int)j0, nb, (int)(j0 + nb), rest, (int)k);
+                // trailing update A22 -= X'X, X = A[j0:j0+nb, j0+nb:]  (upper block tiles only)
+                const double* X = A + j0 + (j0 + nb) * k;
+                gemm(X, k, 1, X, 1, k, A + (j0 + nb) + (j0 + nb) * k, k, rest, rest, nb, -1.0, 1.0, true);
+            }
+        }
+        have_chol = true;
+    }
+
+    // X (k x ncols, leading dimension k) <- R^-1 X, blocked back substitution
+    void back_solve(double* X, int ncols) {
+        const double* A = Mf.as<double>();
+        const long long nblk = (k + kNb - 1) / kNb;
+        for (long long jb = nblk - 1; jb >= 0; --jb) {
+            const long long j0 = jb * kNb;
+            const int nb = (int)std::min<long long>(kNb, k - j0);
+            tri(TRI_BACK, Mf.as<double>(), k, X, k, (int)j0, nb, 0, ncols, (int)k);
+            // X[0:j0, :] -= R[0:j0, j0:j0+nb] Y_j
+            if (j0 > 0) gemm(A + j0 * k, 1, k, X + j0, 1, k, X, k, (int)j0, ncols, nb, -1.0, 1.0);
+        }
+    }
+
+    void sample_dense(const double* Z, int64_t n, double* R, double* L) override {
+        factorize();
+        const int nvec = (int)n;
+        W.ensure(8 * (size_t)k * std::max<long long>(nvec, 1));
+        // W = P Z ; W <- R^-1 W ; residuals = P W
+        VecParams P = vp();
+        P.op = VOP_FLIP; P.nvec = nvec; P.in = Z; P.out = W.as<double>();
+        vec_launch(ctx, rws, P);
+        back_solve(W.as<double>(), nvec);
+        P.in = W.as<double>(); P.out = R;
+        vec_launch(ctx, rws, P);
+        if (L) {
+            // L_Sigma = P R^-1 P: X = R^-1 (back substitution on the identity); reversing the flat
+            // column-major array maps (i, j) -> (k-1-i, k-1-j)
+            Rinv.ensure(8 * k * k);
+            tri(TRI_EYE, Rinv.as<double>(), k, nullptr, 0, 0, kNb, 0, 0, (int)k);
+            back_solve(Rinv.as<double>(), (int)k);
+            VecParams Q = vp();
+            Q.op = VOP_FLIP; Q.N = k * k; Q.in = Rinv.as<double>(); Q.out = L;
+            vec_launch(ctx, rws, Q);
+        }
+    }
+
+    double kl_value_grad(const double* x, const double* R, int64_t n, double* grad) override {
+        const int np = (int)(2 * n);
+        P2.ensure(8 * (size_t)k * np); MP.ensure(8 * (size_t)k * np); gsum.ensure(8 * k);
+        vec_build_samples(ctx, rws, x, R, k, (int)n, P2.as<double>());          // points x +- r_i
+        apply_M(P2.as<double>(), np, MP.as<double>());
+        VecParams Q = vp();
+        Q.op = VOP_QUAD; Q.nvec = np; Q.in = P2.as<double>(); Q.y = MP.as<double>(); Q.Ap = h.as<double>();
+        Q.fin = FIN_TOTAL;
+        vec_launch(ctx, rws, Q);
+        double tot = 0.0;
+        rt_d2h(&tot, rws.red.p, 8, ctx->stream);
+        if (grad) {
+            // grad = mean_p (M p - h)
+            vec_sum_chunks(ctx, rws, MP.as<double>(), k, np, 1.0 / (double)np, gsum.as<double>(), k);
+            vec_axpy(ctx, rws, grad, gsum.as<double>(), -1.0, h.as<double>(), k);
+        }
+        rt_sync(ctx->stream);
+        return tot / (double)np + 0.5 * dd + const_term;
+    }
+
+    void mean_metric_prepare(const double*, const double*, int64_t) override {}   // M does not depend on the point
+    void mean_metric_apply(const double* u, double* out) override { apply_M(u, 1, out); }
+
+    void ncg_init(const double* g) override {
+        const size_t b = 8 * k;
+        n_x.ensure(b); n_r.ensure(b); n_p.ensure(b); n_t.ensure(b);
+        ncgws.ensure(1);
+        ncg_sc = ncgws.scalars(0.0, 1.4901161193847656e-08, k, CG_ITSOLVERS);
+        rt_memset(ncgws.n_active.p, 0, sizeof(int) * 4, ctx->stream);
+        vec_cg_init(ctx, rws, ncg_sc, g, k, n_x.as<double>(), n_r.as<double>(), n_p.as<double>(), k, 1);
+        ncg_first = true;
+    }
+    bool ncg_active() override {
+        rt_d2h(&h_act, ncgws.active.p, sizeof(int), ctx->stream);
+        rt_sync(ctx->stream);
+        return h_act != 0;
+    }
+    void ncg_update() override {
+        if (!ncg_first) {
+            VecParams P = vp();
+            P.op = VOP_CG_PUPD; P.r = n_r.as<double>(); P.p = n_p.as<double>(); P.cg = ncg_sc;
+            vec_launch(ctx, rws, P);
+        }
+        apply_M(n_p.as<double>(), 1, n_t.as<double>());
+        VecParams P = vp();
+        P.op = VOP_CG_PAP; P.p = n_p.as<double>(); P.Ap = n_t.as<double>(); P.cg = ncg_sc; P.fin = FIN_CG_PAP;
+        vec_launch(ctx, rws, P);
+        vec_cg_update(ctx, rws, ncg_sc, n_x.as<double>(), n_r.as<double>(), n_p.as<double>(), n_t.as<double>(), k, 1);
+        ncg_first = false;
+    }
+    const double* ncg_dx() override { return n_x.as<double>(); }
+};
+
+}  // namespace
+
+Engine* make_dense_engine(mgvib200_ctx* ctx, const mgvib200_model_desc& d) {
+    DenseEngine* e = new DenseEngine();
+    e->ctx = ctx;
+    try {
+        e->setup(d);
+    } catch (...) {
+        delete e;
+        throw;
+    }
+    return e;
+}
+
 }  // namespace mgvi

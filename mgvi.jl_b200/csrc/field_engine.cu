@@ -36,12 +36,15 @@ struct FieldEngine : Engine {
     long long dims[3] = {1, 1, 1};
     long long N = 0;
     bool fast = false;
+    bool big = false;           // long 1-D field: four-step split n = n1 * n2 (big1d_pass.h)
+    int lg_n1 = 0, lg_n2 = 0, lg_h = 0;
+    DevBuf data_perm, tlo, thi, cs;
     double c = 1, offset = 0, sigma = 1, inv_sigma2 = 1;
     int link = LINK_EXP, like = LIKE_POISSON, layout = 0;
     long long z1_ld = 0, z1_stride = 1;
     double const_term = 0.0;    // per-point constants of -loglike and of the prior
-    int max_L = 4;
-    int prefetch_waves = 1;     // software L2 prefetch distance in resident-block waves (0 = off)
+    int max_L = 2;              // complex columns per strided tile (2: 512-thread blocks, 2 per SM; measured best at C3)
+    int prefetch_waves = 0;     // software L2 prefetch distance in resident-block waves (0 = off: measured slower at C3, profiles/README.md)
     bool use_hot = true;        // compile-time-shape kernels for the benchmark sizes
 
     DevBuf A, data, w, q, wbar, center;
@@ -93,11 +96,19 @@ struct FieldEngine : Engine {
         fast = true;
         for (int i = 0; i < ndim; ++i)
             if (!is_pow2(dims[i]) || dims[i] < 8 || dims[i] > kFastMaxAxis) fast = false;
+        long long big_min = kFastMaxAxis + 1;     // tests lower this to run the four-step path at small sizes
+        if (const char* e = getenv("MGVIB200_BIG_MIN")) big_min = std::max<long long>(64, atoll(e));
+        if (ndim == 1 && is_pow2(N) && N >= big_min && N <= kFastMaxAxis * kFastMaxAxis) {
+            big = true; fast = true;
+            const int lg = ilog2(N);
+            lg_n1 = (lg + 1) / 2; lg_n2 = lg - lg_n1; lg_h = (lg + 1) / 2;
+        }
         if (N >= (1LL << 31)) fast = false;      // the pass kernels use 32-bit element offsets
         if (const char* e = getenv("MGVIB200_FORCE_GENERIC")) if (atoi(e)) fast = false;
         if (const char* e = getenv("MGVIB200_STRIDED_L")) max_L = std::max(1, atoi(e));
         if (const char* e = getenv("MGVIB200_PREFETCH_WAVES")) prefetch_waves = std::max(0, atoi(e));
         if (const char* e = getenv("MGVIB200_NO_HOT")) use_hot = !atoi(e);
+        if (getenv("MGVIB200_FORCE_GENERIC") && atoi(getenv("MGVIB200_FORCE_GENERIC"))) big = false;
         if (!fast)
             for (int i = 0; i < ndim; ++i)
                 if (dims[i] > kNaiveMaxAxis)
@@ -119,8 +130,11 @@ struct FieldEngine : Engine {
             cl = (double)N * (log(sigma) + 0.5 * log(2.0 * M_PI));
         }
         const_term = cl + 0.5 * (double)N * log(2.0 * M_PI);
-        for (int i = 0; i < ndim; ++i) {
-            const long long n = dims[i];
+        std::vector<long long> lens;
+        if (big) { lens.push_back(1LL << lg_n1); lens.push_back(1LL << lg_n2); }
+        else for (int i = 0; i < ndim; ++i) lens.push_back(dims[i]);
+        for (size_t i = 0; i < lens.size(); ++i) {
+            const long long n = lens[i];
             if (fast) {
                 if (tw.count(n)) continue;
                 // per-stage twiddle runs (fft_core.h): for each radix-8 stage with Ns > 1, W^j, W^2j, W^4j, j < Ns
@@ -155,7 +169,75 @@ struct FieldEngine : Engine {
                 rt_sync(ctx->stream);
             }
         }
+        if (big) {
+            // W_N^e split as W_N^(e_lo) * W_N^(e_hi 2^h); observations in the permuted data-space order
+            const long long nlo = 1LL << lg_h, nhi = N >> lg_h;
+            std::vector<double> a(2 * nlo), b(2 * nhi), dp(N);
+            const long double tp = 2.0L * 3.14159265358979323846264338327950288L;
+            for (long long e = 0; e < nlo; ++e) {
+                long double ang = tp * (long double)e / (long double)N;
+                a[2 * e] = (double)cosl(ang); a[2 * e + 1] = (double)(-sinl(ang));
+            }
+            for (long long e = 0; e < nhi; ++e) {
+                long double ang = tp * (long double)(e << lg_h) / (long double)N;
+                b[2 * e] = (double)cosl(ang); b[2 * e + 1] = (double)(-sinl(ang));
+            }
+            const long long n1 = 1LL << lg_n1, n2 = 1LL << lg_n2;
+            for (long long r = 0; r < n1; ++r)
+                for (long long cc = 0; cc < n2; ++cc) dp[r * n2 + cc] = d.data[r + n1 * cc];
+            tlo.ensure(16 * nlo); thi.ensure(16 * nhi); data_perm.ensure(8 * N);
+            rt_h2d(tlo.p, a.data(), 16 * nlo, ctx->stream);
+            rt_h2d(thi.p, b.data(), 16 * nhi, ctx->stream);
+            rt_h2d(data_perm.p, dp.data(), 8 * N, ctx->stream);
+            rt_sync(ctx->stream);
+        }
         rt_sync(ctx->stream);
+    }
+
+    // ------------------------------------------------------------------------------------------
+    // long 1-D fields (big1d_pass.h)
+    // ------------------------------------------------------------------------------------------
+    template <int KIND, int PRO, int EPI>
+    long long launch_big(FieldPassParams P, int nvec, bool accumulate) {
+        BigParams B;
+        memset(&B, 0, sizeof B);
+        const int npairs = (nvec + 1) / 2;
+        cs.ensure(16 * (size_t)N * npairs);
+        B.lg_n1 = lg_n1; B.lg_n2 = lg_n2; B.lg_h = lg_h;
+        B.cs = cs.as<double2>();
+        B.tw1 = tw.at(1LL << lg_n1).as<double2>(); B.tw2 = tw.at(1LL << lg_n2).as<double2>();
+        B.tlo = tlo.as<double2>(); B.thi = thi.as<double2>();
+        const int lg_len = (KIND == BIG_A || KIND == BIG_AP) ? lg_n1 : lg_n2;
+        int lgL = (KIND == BIG_A) ? 2 : 1;
+        while (lg_len - 3 + lgL > 10) --lgL;                                   // <= 1024 threads per unit
+        if (KIND != BIG_A && lg_len - 3 + lgL > 10) throw RtError{"1-D field too long for the four-step path", 3};
+        B.lgL = lgL;
+        const long long upt = 1LL << (lg_len - 3 + lgL);
+        long long G = std::max<long long>(1, 256 / upt);
+        B.units_per_pair = (KIND == BIG_A) ? ((1LL << lg_n2) >> lgL) : ((KIND == BIG_AP) ? ((1LL << lg_n2) >> 1) : ((1LL << lg_n1) >> 1));
+        G = std::min(G, B.units_per_pair);
+        G = std::max<long long>(G, (32 + upt - 1) / upt);
+        B.G = (int)G;
+        B.npairs = npairs;
+        int npgrp = npairs;
+        B.nloop = 1;
+        if (accumulate) { npgrp = std::min(npairs, 8); B.nloop = (npairs + npgrp - 1) / npgrp; npgrp = (npairs + B.nloop - 1) / B.nloop; }
+        const long long ubl = (B.units_per_pair + G - 1) / G;
+        const long long grid = ubl * npgrp;
+        P.N = N; P.nvec = nvec;
+        if (accumulate) { acc.ensure(sizeof(double) * N * npgrp); P.acc_out = acc.as<double>(); }
+        if (P.fin != FIN_NONE) {
+            const size_t np = (P.fin == FIN_TOTAL) ? (size_t)grid : (size_t)(nvec + 1) * (size_t)ubl;
+            reduce_ws_ensure(rws, ctx, np, (size_t)nvec + 1);
+            P.partials = rws.partials.as<double>(); P.counters = rws.counters.as<unsigned>();
+        }
+        B.f = P;
+        const size_t smem = kSmemHeader + (size_t)G * ((size_t)16 << (lgL + lg_len));
+        ctx->prof_pre(5000 + KIND * 100 + PRO * 10 + EPI);
+        rt_launch(k_big1d<KIND, PRO, EPI>, grid, (int)(G * upt), smem, ctx->stream, B);
+        ctx->prof_post();
+        ctx->launches++;
+        return npgrp;
     }
 
     // ------------------------------------------------------------------------------------------
@@ -359,6 +441,14 @@ struct FieldEngine : Engine {
             chain_generic<PRO, EPI>(P, nvec, false, fin_pro, red_pro, fin_epi, red_epi, accumulate);
             return accumulate ? 1 : 0;
         }
+        if (big) {
+            FieldPassParams Q = P;
+            Q.fin = fin_pro; Q.red_out = red_pro; Q.acc_out = nullptr;
+            launch_big<BIG_A, PRO, EPI_STORE>(Q, nvec, false);
+            FieldPassParams E = P;
+            E.fin = fin_epi; E.red_out = red_epi; E.data = data_perm.as<double>();
+            return launch_big<BIG_B_END, PRO_LOAD, EPI>(E, nvec, accumulate);
+        }
         if (ndim == 1) {
             PassGeo g = geo_axis(0, nvec);
             int nsgrp = 1, nloop = 1;
@@ -406,6 +496,15 @@ struct FieldEngine : Engine {
             chain_generic<PRO, EPI>(P, nvec, false, FIN_NONE, nullptr, fin_epi, red_epi, false);
             return;
         }
+        if (big) {
+            FieldPassParams Q = P;
+            Q.fin = FIN_NONE;
+            launch_big<BIG_B_START, PRO, EPI_STORE>(Q, nvec, false);
+            FieldPassParams E = P;
+            E.fin = fin_epi; E.red_out = red_epi;
+            launch_big<BIG_AP, PRO_LOAD, EPI>(E, nvec, false);
+            return;
+        }
         if (ndim == 1) {
             P.fin = fin_epi; P.red_out = red_epi;
             launch_pass<GEO_PAIRVEC, PRO, EPI, false>(P, geo_axis(0, nvec), nvec, 1, 1);
@@ -434,6 +533,16 @@ struct FieldEngine : Engine {
         P.scale = c * c * pow(0.5, 2 * ndim);
         if (!fast) {
             chain_generic<PRO, EPI_METRIC>(P, nvec, true, FIN_NONE, nullptr, fin, red, false);
+            return;
+        }
+        if (big) {
+            FieldPassParams Q = P;
+            Q.fin = FIN_NONE;
+            launch_big<BIG_A, PRO, EPI_STORE>(Q, nvec, false);
+            launch_big<BIG_B_MID, PRO_LOAD, EPI_STORE>(Q, nvec, false);
+            FieldPassParams E = P;
+            E.fin = fin; E.red_out = red;
+            launch_big<BIG_AP, PRO_LOAD, EPI_METRIC>(E, nvec, false);
             return;
         }
         if (ndim == 1) {
@@ -487,6 +596,17 @@ struct FieldEngine : Engine {
         if (w_host) rt_d2h(w_host, w.p, sizeof(double) * N, ctx->stream);
         if (q_host) rt_d2h(q_host, q.p, sizeof(double) * N, ctx->stream);
         rt_sync(ctx->stream);
+        if (big) {
+            // device order is the permuted data-space order [k1][k2] <-> k = k1 + n1 k2
+            const long long n1 = 1LL << lg_n1, n2 = 1LL << lg_n2;
+            std::vector<double> t(N);
+            for (double* arr : {w_host, q_host}) {
+                if (!arr) continue;
+                for (long long r = 0; r < n1; ++r)
+                    for (long long cc = 0; cc < n2; ++cc) t[r + n1 * cc] = arr[r * n2 + cc];
+                memcpy(arr, t.data(), sizeof(double) * N);
+            }
+        }
     }
 
     void metric_apply(const double* V, int64_t k, double* MV) override {

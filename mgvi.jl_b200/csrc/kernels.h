@@ -1,6 +1,7 @@
 // __global__ entry points (or their emulator stand-ins) for the kernel bodies.
 #pragma once
 #include "vec_ops.h"
+#include "big1d_pass.h"
 
 #if defined(__CUDACC__) && !defined(MGVI_SIMT_EMU)
 #define SIMT_GLOBAL(maxt) __global__ void __launch_bounds__(maxt)
@@ -27,6 +28,12 @@ template <int GEO, int PRO, int EPI, bool DOUBLE, int MAXT, int MINB, int LG, in
 SIMT_GLOBAL2(MAXT, MINB) k_field_pass(SIMT_KARGS(FieldPassParams)) {
     SIMT_SMEM_DECL
     field_pass_body<GEO, PRO, EPI, DOUBLE, LG, LGL, LOOP>(P, simt_smem);
+}
+
+template <int KIND, int PRO, int EPI>
+SIMT_GLOBAL2(1024, 1) k_big1d(SIMT_KARGS(BigParams)) {
+    SIMT_SMEM_DECL
+    big1d_body<KIND, PRO, EPI>(P, simt_smem);
 }
 
 template <int PRO>

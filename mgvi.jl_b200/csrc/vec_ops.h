@@ -14,7 +14,12 @@ enum {
     VOP_AXPY = 3,        // out = x + a * y                                    (nvec = 1)
     VOP_DOT = 4,         // acc = x . y                                        (nvec = 1)
     VOP_BUILD = 5,       // samples[:, 2i] = c + r_i ; samples[:, 2i+1] = c - r_i   (vector = i)
-    VOP_AXPY_INPLACE = 6 // x += a * y                                         (nvec = 1)
+    VOP_AXPY_INPLACE = 6,// x += a * y                                         (nvec = 1)
+    VOP_CG_PUPD = 7,     // p = r + beta p                                     (per vector; dense CG)
+    VOP_CG_PAP = 8,      // acc = p . Ap                                       (per vector; dense CG)
+    VOP_QUAD = 9,        // acc = sum x . (0.5 y - h)  over all vectors         (dense KL value)
+    VOP_FLIP = 10,       // out[i, s] = in[N-1-i, s]                            (index reversal)
+    VOP_COPY = 11        // out = in                                            (per vector)
 };
 
 struct VecParams {
@@ -54,6 +59,13 @@ SIMT_DEVICE void vec_elem(const VecParams& P, int s, long long i, double alpha, 
         case VOP_AXPY: P.out[i] = P.in[i] + P.a * P.y[i]; break;
         case VOP_AXPY_INPLACE: P.out[i] += P.a * P.y[i]; break;
         case VOP_DOT: acc += P.in[i] * P.y[i]; break;
+        case VOP_CG_PUPD: {
+            const_cast<double*>(P.p)[gi] = P.r[gi] + P.cg.beta[s] * P.p[gi];
+        } break;
+        case VOP_CG_PAP: acc += P.p[gi] * P.Ap[gi]; break;
+        case VOP_QUAD: acc += P.in[gi] * (0.5 * P.y[gi] - P.Ap[i]); break;
+        case VOP_FLIP: P.out[gi] = P.in[(long long)s * P.N + (P.N - 1 - i)]; break;
+        case VOP_COPY: P.out[gi] = P.in[(long long)s * P.in_ld + i]; break;
         case VOP_BUILD: {
             const double c = P.in[i], rv = P.y[gi];
             P.out[(long long)(2 * s) * P.N + i] = c + rv;
@@ -68,9 +80,9 @@ SIMT_DEVICE void vec_body(const VecParams& P, unsigned char* smem_raw) {
     int* flag = reinterpret_cast<int*>(smem_raw + 256);
     const int s = (int)(SIMT_BID % P.nvec);
     const long long chunk = SIMT_BID / P.nvec;
-    const bool cg_op = (P.op == VOP_CG_UPDATE);
+    const bool cg_op = (P.op == VOP_CG_UPDATE || P.op == VOP_CG_PUPD || P.op == VOP_CG_PAP);
     if (cg_op && !P.cg.active[s]) return;
-    const double alpha = cg_op ? P.cg.alpha[s] : 0.0;
+    const double alpha = (P.op == VOP_CG_UPDATE) ? P.cg.alpha[s] : 0.0;
     const long long lo = chunk * P.per_block;
     long long hi = lo + P.per_block;
     if (hi > P.N) hi = P.N;

@@ -183,3 +183,44 @@ def check_poly_ops(pkg, ctx, cfg):
         out[key] = rel(res.samples[:, 0::2] - res.samples[:, 1::2], ref["samples"][:, 0::2] - ref["samples"][:, 1::2])
     m.close()
     return out
+
+
+def check_dense_ops(pkg, ctx, cfg, with_step=True):
+    """Dense-linear model (BASELINE.json configs[3] shape): metric, CG sampler, MatrixInversion
+    sampler (and L_Sigma itself), KL value / gradient, mean metric, steps in both sampler modes."""
+    import ctypes as C  # noqa: F401
+    m = pkg.model_from_config(cfg, ctx)
+    om = oracle_model(cfg)
+    c, n = cfg["center"], cfg["n_residuals"]
+    out = {}
+    s = pkg.ResidualSampler(m, c, pkg.B200CG(abstol=0.0, reltol=1e-12, maxiters=10 * m.n_theta), ctx)
+    lin = om.linearize(c)
+    V = np.random.default_rng(5).standard_normal((m.n_theta, 3))
+    out["metric"] = rel(s.metric_apply(V), np.stack([O.metric_apply(lin, V[:, i]) for i in range(3)], axis=1))
+    R, info = pkg.sample_residuals(s, n, draws=(cfg["Z1"], cfg["Z2"]), return_info=True)
+    Ro, ito, _ = O.sample_residuals_cg(om, c, cfg["Z1"], cfg["Z2"], atol=0.0, rtol=1e-12, itmax=10 * m.n_theta)
+    out["residuals"] = rel(R, Ro)
+    out["iters"] = (info["iters"].tolist(), ito.tolist())
+    Z = np.asfortranarray(cfg["Z"])
+    Rd = np.empty((m.n_theta, n), order="F")
+    L = np.empty((m.n_theta, m.n_theta), order="F")
+    ctx.check(ctx.lib.sample_residuals_dense(m.handle, pkg.capi.ptr(Z), n, pkg.capi.ptr(Rd), pkg.capi.ptr(L)))
+    Rdo, Lo = O.sample_residuals_dense(om, c, cfg["Z"])
+    out["dense"] = rel(Rd, Rdo)
+    out["L"] = rel(L, Lo)
+    out["L_lower"] = float(np.abs(np.triu(L, 1)).max())
+    f, g = pkg.kl_value_grad(m, c, Ro)
+    out["kl"] = abs(f - O.mean_neg_log_pstr(om, Ro, c)) / abs(f)
+    out["grad"] = rel(g, O.kl_gradient(om, Ro, c))
+    u = np.random.default_rng(6).standard_normal(m.n_theta)
+    out["mean_metric"] = rel(pkg.mean_metric_apply(m, c, Ro, u), O.mean_metric_apply(om, Ro, c, u))
+    if with_step:
+        res, cn = pkg.mgvi_step(m, cfg["data"], n, c, pkg.MGVIConfig(linsolver=pkg.MatrixInversion()), ctx, draws=cfg["Z"])
+        ref = O.mgvi_step(om, c, Z=cfg["Z"], dense=True)
+        tr, otr = res.info["optimizer_output"], ref["trace"]
+        assert_step_parity(cfg, rel(cn, ref["center"]), rel(res.samples, ref["samples"]),
+                           tr["cg_updates"] == otr.cg_updates and tr["f_calls"] == otr.f_calls, Z=cfg["Z"], dense=True)
+        out["dense_step_residuals"] = rel(res.samples[:, 0::2] - res.samples[:, 1::2],
+                                          ref["samples"][:, 0::2] - ref["samples"][:, 1::2])
+    m.close()
+    return out

@@ -34,6 +34,7 @@ struct Runtime {
     long long bid = 0, nbid = 0;
     std::function<void()> body;
     double warp_f64[64][32];
+    double warp_f64b[64][32];
     int warp_i32[64][32];
     static constexpr size_t kStack = 256 * 1024;
 };
@@ -65,6 +66,27 @@ inline double shfl_xor_f64(double v, int mask) {
     double out = (src < warp_size) ? r.warp_f64[w][src] : v;
     warp_barrier();
     return out;
+}
+
+inline double shfl_idx_f64(double v, int lane) {
+    Runtime& r = rt();
+    int t = tid(), w = t / 32, l = t % 32;
+    r.warp_f64[w][l] = v;
+    warp_barrier();
+    double out = r.warp_f64[w][lane];
+    warp_barrier();
+    return out;
+}
+
+// all lanes publish (a, b); every lane gets the whole warp's values (2 barriers instead of 2 per shuffle)
+inline void warp_allgather2(double a, double b, double (&oa)[32], double (&ob)[32]) {
+    Runtime& r = rt();
+    int t = tid(), w = t / 32, l = t % 32;
+    r.warp_f64[w][l] = a;
+    r.warp_f64b[w][l] = b;
+    warp_barrier();
+    for (int i = 0; i < 32; ++i) { oa[i] = r.warp_f64[w][i]; ob[i] = r.warp_f64b[w][i]; }
+    warp_barrier();
 }
 
 inline int shfl_idx_i32(int v, int lane) {

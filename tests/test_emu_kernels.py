@@ -126,3 +126,24 @@ def test_polyfit_reference_model(pkg, emu_ctx, layout):
     assert out["iters_default"][0] == out["iters_default"][1] == [5] * 4
     assert out["residuals"] < 1e-8, out
     assert out["cg_step"] < 1e-8 and out["dense_step"] < 1e-9, out
+
+
+def test_dense_linear_model(pkg, emu_ctx):
+    """FullJacobianFunc + FullResidualSampler shape (dense J, MatrixInversion) at a size the
+    emulator handles; tile edges are exercised (96 x 40 does not fill a 128 x 128 x 16 tile)."""
+    from helpers import check_dense_ops
+    cfg = pkg.synthetic.dense_linear_config(96, 40, 3)
+    out = check_dense_ops(pkg, emu_ctx, cfg)
+    for k in ("metric", "residuals", "dense", "L", "kl", "grad", "mean_metric", "dense_step_residuals"):
+        assert out[k] < 1e-10, (k, out)
+    assert out["L_lower"] == 0.0
+    assert out["iters"][0] == out["iters"][1]
+
+
+@pytest.mark.parametrize("N,like,layout", [(64, "LIKE_POISSON", None), (128, "LIKE_NORMAL", 2), (1024, "LIKE_POISSON", None)])
+def test_long_1d_four_step_path(pkg, emu_ctx, monkeypatch, N, like, layout):
+    """The four-step split used for 1-D fields longer than 4096 pixels (BASELINE.json configs[1],
+    2^16 pixels), forced on at small sizes: n = n1 * n2 with both square and non-square splits."""
+    monkeypatch.setenv("MGVIB200_BIG_MIN", "64")
+    cfg = _field(pkg, (N,), like, 3, layout)
+    assert_field_ops(check_field_ops(pkg, emu_ctx, cfg, check_step=True), cfg)

@@ -187,3 +187,49 @@ def test_polyfit_model(pkg, gpu_ctx, layout, reference_grid):
     assert out["iters_default"][0] == out["iters_default"][1] == [5] * 8
     assert out["residuals"] < 1e-8, out
     assert out["cg_step"] < 1e-8 and out["dense_step"] < 1e-9, out
+
+
+@pytest.mark.parametrize("m,k,n", [(96, 40, 3), (700, 300, 5), (2048, 1024, 8)])
+def test_dense_linear_model(pkg, gpu_ctx, m, k, n):
+    """BASELINE.json configs[3] family: dense J, FP64 tensor-core J'FJ, blocked Cholesky, both
+    samplers, against the oracle (LAPACK)."""
+    from helpers import check_dense_ops
+    cfg = pkg.synthetic.dense_linear_config(m, k, n)
+    out = check_dense_ops(pkg, gpu_ctx, cfg, with_step=(k <= 300))
+    for key in ("metric", "residuals", "dense", "L", "kl", "grad", "mean_metric"):
+        assert out[key] < 1e-10, (key, out)
+    assert out["L_lower"] == 0.0
+    assert all(abs(a - b) <= 2 for a, b in zip(*out["iters"]))
+
+
+def test_dense_c4_full_size_properties(pkg, gpu_ctx):
+    """C4 itself (J 16384 x 4096): L_Sigma is lower triangular with L L' M = I on probe vectors, and
+    the residuals are L_Sigma Z."""
+    cfg = pkg.synthetic.dense_linear_config(16384, 4096, 4)
+    m = pkg.model_from_config(cfg, gpu_ctx)
+    sd = pkg.ResidualSampler(m, cfg["center"], pkg.MatrixInversion(), gpu_ctx)
+    Z = np.asfortranarray(cfg["Z"])
+    R = np.empty((4096, 4), order="F")
+    L = np.empty((4096, 4096), order="F")
+    gpu_ctx.check(gpu_ctx.lib.sample_residuals_dense(m.handle, pkg.capi.ptr(Z), 4, pkg.capi.ptr(R), pkg.capi.ptr(L)))
+    assert np.abs(np.triu(L, 1)).max() == 0.0
+    assert rel(R, L @ Z) < 1e-12
+    V = np.random.default_rng(1).standard_normal((4096, 2))
+    MV = sd.metric_apply(V)                                  # M V
+    assert rel(L @ (L.T @ MV), V) < 1e-10                    # (L L') M = I
+    J = cfg["J"]
+    assert rel(MV, V + J.T @ (J @ V) / cfg["sigma"] ** 2) < 1e-11
+    m.close()
+
+
+def test_c2_1d_65536_poisson(pkg, gpu_ctx):
+    """BASELINE.json configs[1]: 1-D field of 2^16 pixels, Poisson counts, 16 residual samples
+    (four-step transform path), every row of the path against the oracle."""
+    cfg = _field(pkg, (65536,), "LIKE_POISSON", 16)
+    assert_field_ops(check_field_ops(pkg, gpu_ctx, cfg, check_step=True), cfg)
+
+
+@pytest.mark.parametrize("N", [8192, 32768, 1 << 20])
+def test_long_1d_other_lengths(pkg, gpu_ctx, N):
+    cfg = _field(pkg, (N,), "LIKE_NORMAL", 3, layout=2)
+    assert_field_ops(check_field_ops(pkg, gpu_ctx, cfg, check_step=(N <= 32768)), cfg)

@@ -1,0 +1,61 @@
+"""C4 (BASELINE.json configs[3]): dense J 16384 x 4096, FullJacobianFunc + FullResidualSampler.
+Times the FP64 tensor-core J'FJ assembly, the blocked Cholesky and the residual sampling with the
+library's per-kernel CUDA-event profile, and prints one JSON line."""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as g  # noqa: E402
+
+
+def profile(ctx, fn):
+    lib = ctx.lib
+    lib.profile_begin(ctx.handle)
+    t0 = time.perf_counter()
+    out = fn()
+    tags = (C.c_int32 * 64)(); ms = (C.c_double * 64)(); cnt = (C.c_int64 * 64)()
+    n = lib.profile_end(ctx.handle, 64, tags, ms, cnt)
+    wall = time.perf_counter() - t0
+    return out, {int(tags[i]): (float(ms[i]), int(cnt[i])) for i in range(max(n, 0))}, wall
+
+
+def main():
+    m = int(os.environ.get("DENSE_M", 16384)); k = int(os.environ.get("DENSE_K", 4096)); n = 32
+    pkg = g.load_package()
+    cfg = pkg.synthetic.dense_linear_config(m, k, n)
+    ctx = pkg.MGVIContext(device=0)
+    model, prof_c, wall_c = profile(ctx, lambda: pkg.model_from_config(cfg, ctx))
+    syrk_ms = prof_c.get(3001, (0, 0))[0]
+    sd = pkg.ResidualSampler(model, cfg["center"], pkg.MatrixInversion(), ctx)
+    Z = np.asfortranarray(cfg["Z"]); R = np.empty((k, n), order="F")
+    def run():
+        ctx.check(ctx.lib.sample_residuals_dense(model.handle, pkg.capi.ptr(Z), n, pkg.capi.ptr(R), None))
+    _, prof_s, wall_s = profile(ctx, run)          # first call factorises
+    _, prof_s2, wall_s2 = profile(ctx, run)        # factor cached: back substitution only
+    chol_ms = sum(v[0] for t, v in prof_s.items()) - sum(v[0] for t, v in prof_s2.items())
+    trail_ms = prof_s.get(3001, (0, 0))[0]
+    res, c_new = pkg.mgvi_step(model, cfg["data"], n, cfg["center"], pkg.MGVIConfig(linsolver=pkg.MatrixInversion()), ctx,
+                               draws=cfg["Z"])
+    t0 = time.perf_counter()
+    res, c_new = pkg.mgvi_step(model, cfg["data"], n, cfg["center"], pkg.MGVIConfig(linsolver=pkg.MatrixInversion()), ctx,
+                               draws=cfg["Z"])
+    step_s = time.perf_counter() - t0
+    full = 2.0 * m * k * k
+    out = {"workload": "c4: dense J %d x %d, Normal(0.5), %d residuals, MatrixInversion sampler" % (m, k, n),
+           "syrk_ms": syrk_ms, "syrk_tflops_symmetric_half": 0.5 * full / (syrk_ms * 1e-3) / 1e12 if syrk_ms else None,
+           "syrk_tflops_full_product_equivalent": full / (syrk_ms * 1e-3) / 1e12 if syrk_ms else None,
+           "cholesky_ms": chol_ms, "cholesky_tflops": (k ** 3 / 3.0) / (chol_ms * 1e-3) / 1e12 if chol_ms > 0 else None,
+           "cholesky_trailing_update_ms": trail_ms, "sample_ms_after_factor": sum(v[0] for v in prof_s2.values()),
+           "model_create_wall_s": wall_c, "mgvi_step_s": step_s, "mnlp": res.mnlp,
+           "kernels_create": prof_c, "kernels_first_sample": prof_s}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
