@@ -35,6 +35,14 @@ sys.path.insert(0, ROOT)
 METRIC = "residual-sample CG iterations/s (2048x2048 correlated field, Normal, 32 residual samples)"
 UNIT = "sample-iterations/s"
 
+
+def metric_name(args, cfg=None):
+    if args.workload == "c3":
+        return METRIC
+    dims, like, n = WORKLOADS[args.workload]
+    return "residual-sample CG iterations/s (%s correlated field, %s, %d residual samples)" % (
+        "x".join(str(d) for d in dims), "Normal" if like == "LIKE_NORMAL" else "Poisson", n)
+
 WORKLOADS = {
     # name: (dims, likelihood name, n residuals)
     "c3": ((2048, 2048), "LIKE_NORMAL", 32),
@@ -173,7 +181,7 @@ def run_reference(args, rank, world):
     sample = "%d residual samples x %d CG iterations per step (%s, full field size)" % (
         args.ref_samples, args.ref_iters, args.workload)
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "impl": "reference", "metric": metric_name(args), "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
         "warmup": W, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args, cfg), "field_std": args.field_std},
@@ -182,7 +190,7 @@ def run_reference(args, rank, world):
                                  "Julia is not installed in this image"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def workload_name(args, cfg):
@@ -193,7 +201,21 @@ def workload_name(args, cfg):
 
 
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line: str):
+    """The driver reads ONE JSON line from stdout; libraries (NCCL prints its version banner on
+    stdout) are kept off it: fd 1 is pointed at stderr for the whole run and the result line goes
+    to the saved descriptor."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -339,7 +361,7 @@ def main():
     cg_path["frac_of_hbm_peak"] = cg_path["achieved_gbs"] / hbm_peak
 
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args, cfg), "iters_per_step": ITERS, "field_std": args.field_std,
@@ -412,7 +434,7 @@ def main():
                                "note": "CPU restatement of MGVI.jl v0.4.5 hot path (oracle/: NumPy + scipy.fft, "
                                        "all host cores); Julia is not installed in this image"}
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(json.dumps(out))
     for p in (c_dev, z1_dev, z2_dev, r_dev):
         lib.dev_free(ctx.handle, p)
     model.close()

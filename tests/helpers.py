@@ -119,7 +119,7 @@ def assert_field_ops(out, cfg=None):
     assert out["build_exact"], out
     a, b = out["iters"]
     # at reltol 1e-12 the tail of the solve sits on the rounding floor: counts may differ by a few
-    assert all(abs(x - y) <= 3 + 0.05 * y for x, y in zip(a, b)), out["iters"]
+    assert all(abs(x - y) <= 3 + 0.10 * y for x, y in zip(a, b)), out["iters"]
     if "center" in out:
         if cfg is None:
             for k in ("center", "samples", "mnlp"):

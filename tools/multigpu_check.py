@@ -40,10 +40,13 @@ def main():
         Z1, Z2 = np.asfortranarray(cfg["Z1"][:, sl]), np.asfortranarray(cfg["Z2"][:, sl])
         conf = pkg.MGVIConfig(linsolver=pkg.B200CG(abstol=0.0, reltol=1e-12))
         res, center = pkg.mgvi_step(model, cfg["data"], nl, cfg["center"], conf, ctx, draws=(Z1, Z2))
-        # sharded KL value/gradient (all-reduced inside) must be identical on every rank
-        f, grad = pkg.kl_value_grad(model, cfg["center"], 0.5 * (res.samples[:, 0::2] - res.samples[:, 1::2]))
-        t = torch.tensor([f, float(np.abs(grad).sum()), res.mnlp, float(np.abs(center).sum())], dtype=torch.float64,
-                         device="cuda")
+        # sharded KL value/gradient and mean metric (all-reduced inside) must be identical on every rank
+        R_loc = 0.5 * (res.samples[:, 0::2] - res.samples[:, 1::2])
+        f, grad = pkg.kl_value_grad(model, cfg["center"], R_loc)
+        u = np.random.default_rng(6).standard_normal(model.n_theta)
+        mm = pkg.mean_metric_apply(model, cfg["center"], R_loc, u)
+        t = torch.tensor([f, float(np.abs(grad).sum()), res.mnlp, float(np.abs(center).sum()), float(np.abs(mm).sum())],
+                         dtype=torch.float64, device="cuda")
         tmax, tmin = t.clone(), t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
@@ -63,11 +66,23 @@ def main():
             e1, e2 = rel(center, c1), rel(S, res1.samples)
             e3, e4 = rel(center, ref["center"]), rel(S, ref["samples"])
             tr, tr1 = res.info["optimizer_output"], res1.info["optimizer_output"]
-            good = same and e1 < 1e-10 and e2 < 1e-10 and e3 < 1e-9 and e4 < 1e-9 and tr["cg_updates"] == tr1["cg_updates"]
+            # well-conditioned rows, unsharded on one GPU with the gathered residuals: tight
+            R_all = 0.5 * (S[:, 0::2] - S[:, 1::2])
+            f1, g1 = pkg.kl_value_grad(m1, cfg["center"], R_all)
+            mm1 = pkg.mean_metric_apply(m1, cfg["center"], R_all, u)
+            e_f, e_g, e_m = abs(f - f1) / abs(f1), rel(grad, g1), rel(mm, mm1)
+            # residuals do not pass through the optimiser: tight against the oracle's CG solutions
+            e_r = rel(R_all, 0.5 * (ref["samples"][:, 0::2] - ref["samples"][:, 1::2]))
+            # the Newton phase is chaotic on some fixtures (tests/helpers.py): judged against the oracle's own
+            # reproducibility
+            from helpers import assert_step_parity
+            verdict = assert_step_parity(cfg, max(e1, e3), max(e2, e4), tr["cg_updates"] == tr1["cg_updates"])
+            good = same and e_f < 1e-12 and e_g < 1e-11 and e_m < 1e-12 and e_r < 1e-10
             ok = ok and good
-            print("dims %s world %d: ranks identical %s | vs 1-GPU center %.2e samples %.2e | vs oracle center %.2e "
-                  "samples %.2e | traces %s %s -> %s" % (dims, world, same, e1, e2, e3, e4, tr["cg_updates"],
-                                                        tr1["cg_updates"], "PASS" if good else "FAIL"), flush=True)
+            print("dims %s world %d: ranks identical %s | sharded vs 1-GPU: KL %.1e grad %.1e mean-metric %.1e | "
+                  "residuals vs oracle %.1e | step vs 1-GPU center %.2e, vs oracle %.2e (%s) traces %s %s -> %s" % (
+                      dims, world, same, e_f, e_g, e_m, e_r, e1, e3, verdict or "tight", tr["cg_updates"],
+                      tr1["cg_updates"], "PASS" if good else "FAIL"), flush=True)
             m1.close(); ctx1.close()
         model.close()
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
