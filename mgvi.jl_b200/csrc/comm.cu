@@ -72,6 +72,13 @@ void comm_init(mgvib200_ctx* ctx, int rank, int world, const uint8_t idb[128]) {
     ctx->comm = c;
     ctx->rank = rank;
     ctx->world = world;
+    // NCCL connects lazily on the first collective (hundreds of ms): pay that here, not inside the
+    // first Newton step
+    double* d = (double*)rt_malloc(sizeof(double) * 8);
+    rt_memset(d, 0, sizeof(double) * 8, ctx->stream);
+    comm_allreduce_sum(ctx, d, 8);
+    rt_sync(ctx->stream);
+    rt_free(d);
 }
 
 void comm_destroy(mgvib200_ctx* ctx) {

@@ -46,6 +46,7 @@ struct FieldEngine : Engine {
     int max_L = 2;              // complex columns per strided tile (2: 512-thread blocks, 2 per SM; measured best at C3)
     int prefetch_waves = 0;     // software L2 prefetch distance in resident-block waves (0 = off: measured slower at C3, profiles/README.md)
     bool use_hot = true;        // compile-time-shape kernels for the benchmark sizes
+    int prefetch_epi = 0;       // L1 hints for post-transform operands (MGVIB200_PREFETCH_EPI)
 
     DevBuf A, data, w, q, wbar, center;
     std::map<long long, DevBuf> tw, cas;
@@ -108,6 +109,7 @@ struct FieldEngine : Engine {
         if (const char* e = getenv("MGVIB200_STRIDED_L")) max_L = std::max(1, atoi(e));
         if (const char* e = getenv("MGVIB200_PREFETCH_WAVES")) prefetch_waves = std::max(0, atoi(e));
         if (const char* e = getenv("MGVIB200_NO_HOT")) use_hot = !atoi(e);
+        if (const char* e = getenv("MGVIB200_PREFETCH_EPI")) prefetch_epi = atoi(e);
         if (getenv("MGVIB200_FORCE_GENERIC") && atoi(getenv("MGVIB200_FORCE_GENERIC"))) big = false;
         if (!fast)
             for (int i = 0; i < ndim; ++i)
@@ -327,6 +329,7 @@ struct FieldEngine : Engine {
         } else {
             grid = g.ntb * nsgrp;
         }
+        P.prefetch_epi = prefetch_epi;
         // prefetch distance: what one wave of resident blocks covers (blocks/SM from the thread count)
         {
             const int per_sm = g.threads <= 256 ? MGVI_MINB : (g.threads <= 512 ? 2 : 1);

@@ -69,6 +69,7 @@ struct FieldPassParams {
     int link, likelihood, first_iter, want_grad;
     int mask_active;                          // skip vectors whose cg.active flag is 0 (CG iterations only)
     int prefetch_blocks;                      // > 0: hint the inputs of block (this + prefetch_blocks) into L2
+    int prefetch_epi;                         // hint the epilogue / mid operands into L1 before the transform
     // ---- reduction ------------------------------------------------------------------------
     int fin;
     double* partials; unsigned* counters; double* red_out;
@@ -521,6 +522,22 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
         } else {
 #pragma unroll
             for (int m = 0; m < 8; ++m) v[m] = make_double2(0.0, 0.0);
+        }
+        // operands only needed AFTER the transform (the "+ v" term, the mid weight): start them towards
+        // L1 now -- a hint costs no register and no scoreboard entry, the later load then hits
+        if (P.prefetch_epi && valid && !pairvec) {
+            if (EPI == EPI_METRIC) {
+                const double* q = P.vin + (long long)sa * P.vin_ld;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    SIMT_PREFETCH_L1(q + off_a + m * step);
+                    if (GEO != GEO_STRIDED) SIMT_PREFETCH_L1(q + off_b + m * step);
+                }
+            }
+            if (DOUBLE) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) SIMT_PREFETCH_L1(P.w + off_a + m * step);
+            }
         }
         if (it > 0) SIMT_SYNC();   // previous iteration's combine reads vs this iteration's writes
         fft_line_forward<LG>(v, lv, lt, log2n, P.tw);

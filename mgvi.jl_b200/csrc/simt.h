@@ -30,6 +30,7 @@
 #define SIMT_PREFETCH_BULK_L2(ptr, bytes)                                                          \
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"((unsigned)(bytes)) : "memory")
 #define SIMT_PREFETCH_L2(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))
+#define SIMT_PREFETCH_L1(ptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr))
 // optimisation fence on a 32-bit value: stops the compiler from precomputing (and spilling) the
 // addresses of a later phase at the top of the kernel
 #define SIMT_OPAQUE_U32(x) asm volatile("" : "+r"(x))
@@ -59,6 +60,7 @@
 #define SIMT_LDCG(p) (*(p))
 #define SIMT_PREFETCH_BULK_L2(ptr, bytes) ((void)0)
 #define SIMT_PREFETCH_L2(ptr) ((void)0)
+#define SIMT_PREFETCH_L1(ptr) ((void)0)
 #define SIMT_OPAQUE_U32(x) ((void)0)
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
