@@ -121,25 +121,19 @@ void strong_wolfe(const Fn1& phi, const Fn1& dphi, double alpha0, double phi0, d
 // MGVI._optimize(f, adsel, Sigma_bar_inv, x0, ::NewtonCG, opts) -- src/newtoncg.jl:85-167
 // All pointers device.  x_out may alias nothing else.
 // ----------------------------------------------------------------------------------------------
-struct NewtonWs {
-    DevBuf x, g, trial, gt;
-    ReduceWs rws;
-    void release() { x.release(); g.release(); trial.release(); gt.release(); rws.partials.release(); rws.counters.release(); rws.red.release(); }
-};
-
 void newtoncg_dev(mgvib200_model* m, const double* x0, const double* R, int64_t n,
                   const mgvib200_newtoncg_opts& o, double* x_out, double* f_out, mgvib200_newtoncg_trace* tr_out) {
     Engine* E = m->eng;
     mgvib200_ctx* ctx = m->ctx;
     const long long N = E->n_theta;
     need(o.steps >= 0 && o.steps <= MGVIB200_TRACE_MAX, "NewtonCG: steps must be in [0, 64]");
-    static thread_local NewtonWs ws;
     const size_t b = sizeof(double) * N;
-    ws.x.ensure(b); ws.g.ensure(b); ws.trial.ensure(b); ws.gt.ensure(b);
-    double* x = ws.x.as<double>();
-    double* g = ws.g.as<double>();
-    double* trial = ws.trial.as<double>();
-    double* gt = ws.gt.as<double>();
+    ctx->nw_x.ensure(b); ctx->nw_g.ensure(b); ctx->nw_trial.ensure(b); ctx->nw_gt.ensure(b);
+    double* x = ctx->nw_x.as<double>();
+    double* g = ctx->nw_g.as<double>();
+    double* trial = ctx->nw_trial.as<double>();
+    double* gt = ctx->nw_gt.as<double>();
+    ReduceWs& drws = ctx->drv_rws;
     mgvib200_newtoncg_trace tr;
     memset(&tr, 0, sizeof tr);
     rt_event_record(ctx->ev0, ctx->stream);
@@ -167,7 +161,7 @@ void newtoncg_dev(mgvib200_model* m, const double* x0, const double* R, int64_t 
             double f_km1 = f_prev;
             while (E->ncg_active()) {
                 E->ncg_update(); ++k;
-                vec_axpy(ctx, ws.rws, trial, x, -1.0, E->ncg_dx(), N);
+                vec_axpy(ctx, drws, trial, x, -1.0, E->ncg_dx(), N);
                 const double f_k = f(trial);
                 if (k >= o.i1 || fabs(f_k - f_km1) < o.alpha * df_n) {
                     tr.cg_iterations[tr.n_cg_iterations++] = k;
@@ -180,26 +174,25 @@ void newtoncg_dev(mgvib200_model* m, const double* x0, const double* R, int64_t 
         const double* dx = E->ncg_dx();
         if (k == 0) {
             // the iterator yielded nothing: dx = 0 (cg_iterator! zeroes it)
-            static thread_local DevBuf zero;
-            zero.ensure(b);
-            rt_memset(zero.p, 0, b, ctx->stream);
-            dx = zero.as<double>();
+            ctx->nw_zero.ensure(b);
+            rt_memset(ctx->nw_zero.p, 0, b, ctx->stream);
+            dx = ctx->nw_zero.as<double>();
         }
         // line search along d = -dx (linesearch_args, :64-71): phi(a) = f(x + a d), phi'(a) = grad f(x + a d) . d
-        const double dphi0 = -vec_dot(ctx, ws.rws, g, dx, N);
+        const double dphi0 = -vec_dot(ctx, drws, g, dx, N);
         Fn1 phi = [&](double a) {
-            vec_axpy(ctx, ws.rws, trial, x, -a, dx, N);
+            vec_axpy(ctx, drws, trial, x, -a, dx, N);
             return f(trial);
         };
         Fn1 dphi = [&](double a) {
-            vec_axpy(ctx, ws.rws, trial, x, -a, dx, N);
+            vec_axpy(ctx, drws, trial, x, -a, dx, N);
             gradf(trial, gt);
-            return -vec_dot(ctx, ws.rws, gt, dx, N);
+            return -vec_dot(ctx, drws, gt, dx, N);
         };
         double beta = 0.0;
         strong_wolfe(phi, dphi, 1.0, f_prev, dphi0, beta, f_n);      // :142
         tr.step_lengths[step - 1] = beta;
-        vec_axpy_inplace(ctx, ws.rws, x, -beta, dx, N);              // :143
+        vec_axpy_inplace(ctx, drws, x, -beta, dx, N);              // :143
         df_n = fabs(f_n - f_prev);                                   // :144
         f_prev = f_n;
         tr.f_history[step] = f_n;                                    // :146
@@ -222,10 +215,9 @@ void step_dev(mgvib200_model* m, const double* center, const double* Z1, const d
     const long long N = E->n_theta;
     E->linearize(center);                                            // ResidualSampler ctor, :133
     m->linearized = true;
-    static thread_local DevBuf Rbuf, ReduceDummy;
-    static thread_local ReduceWs rws;
-    Rbuf.ensure(sizeof(double) * N * n);
-    double* R = Rbuf.as<double>();
+    ReduceWs& rws = m->ctx->drv_rws;
+    m->ctx->step_R.ensure(sizeof(double) * N * n);
+    double* R = m->ctx->step_R.as<double>();
     if (dense) {
         E->sample_dense(Z1, n, R, nullptr);                          // :134 with MatrixInversion
         if (iters_host) for (int64_t i = 0; i < n; ++i) iters_host[i] = 0;
@@ -276,6 +268,12 @@ int mgvib200_init(int device_id, mgvib200_ctx** out) {
 void mgvib200_destroy(mgvib200_ctx* ctx) {
     if (!ctx) return;
     comm_destroy(ctx);
+    try { rt_set_device(ctx->device); } catch (...) {}
+    for (mgvi::DevBuf* b : {&ctx->nw_x, &ctx->nw_g, &ctx->nw_trial, &ctx->nw_gt, &ctx->nw_zero, &ctx->step_R,
+                            &ctx->count_scalar})
+        b->release();
+    ctx->drv_rws.release();
+    for (auto e : ctx->ev_pool) rt_event_destroy(e);
     rt_host_free(ctx->h_pinned);
     rt_event_destroy(ctx->ev0);
     rt_event_destroy(ctx->ev1);
@@ -498,8 +496,7 @@ int mgvib200_build_samples(mgvib200_model* m, const double* center, const double
         double* cd = stage_in(m, 0, center, nt);
         double* rd = stage_in(m, 3, R, nt * n);
         double* sd = stage_out(m, 7, nt * 2 * n);
-        static thread_local ReduceWs rws;
-        vec_build_samples(m->ctx, rws, cd, rd, (long long)nt, (int)n, sd);
+        vec_build_samples(m->ctx, m->ctx->drv_rws, cd, rd, (long long)nt, (int)n, sd);
         rt_d2h(samples, sd, sizeof(double) * nt * 2 * n, m->ctx->stream);
         rt_sync(m->ctx->stream);
     });

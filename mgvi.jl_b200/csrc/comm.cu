@@ -98,8 +98,8 @@ void comm_allreduce_sum(mgvib200_ctx* ctx, double* dev, long long count) {
 
 int64_t comm_global_count(mgvib200_ctx* ctx, int64_t local) {
     if (!ctx->comm || ctx->world <= 1) return local;
-    static thread_local double* d = nullptr;
-    if (!d) d = (double*)rt_malloc(sizeof(double));
+    ctx->count_scalar.ensure(sizeof(double));
+    double* d = ctx->count_scalar.as<double>();
     double h = (double)local;
     rt_h2d(d, &h, sizeof(double), ctx->stream);
     comm_allreduce_sum(ctx, d, 1);

@@ -26,6 +26,15 @@ struct DevBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// reduction scratch shared by all kernels of a model
+struct ReduceWs {
+    DevBuf partials;   // doubles
+    DevBuf counters;   // unsigned, zero-initialised, self-resetting
+    DevBuf red;        // doubles: small result slots
+    size_t ncounters = 0;
+    void release() { partials.release(); counters.release(); red.release(); ncounters = 0; }
+};
+
 }  // namespace mgvi
 
 struct mgvib200_ctx {
@@ -40,6 +49,10 @@ struct mgvib200_ctx {
     int64_t lockstep_iters = 0;
     int* h_pinned = nullptr;        // small pinned staging area (64 KB)
     int sm_count = 148;
+    // per-context device scratch of the model-independent drivers (Newton-CG, mgvi_step): owned by the
+    // context so that several contexts (devices) can live in one process
+    mgvi::DevBuf nw_x, nw_g, nw_trial, nw_gt, nw_zero, step_R, count_scalar;
+    mgvi::ReduceWs drv_rws;
     // per-kernel timing (bench.py roofline): CUDA events around every launch while enabled
     bool profile = false;
     struct ProfRec { int tag; mgvi::rt_event a, b; };
@@ -63,14 +76,6 @@ struct mgvib200_ctx {
 };
 
 namespace mgvi {
-
-// reduction scratch shared by all kernels of a model
-struct ReduceWs {
-    DevBuf partials;   // doubles
-    DevBuf counters;   // unsigned, zero-initialised, self-resetting
-    DevBuf red;        // doubles: small result slots
-    size_t ncounters = 0;
-};
 
 struct CgWs {
     int nvec = 0;

@@ -53,15 +53,10 @@ template <typename K, typename P>
 inline void rt_launch(K kernel, long long grid, int block, size_t smem, rt_stream s, const P& params) {
     if (grid <= 0) return;
     if (grid > 2147483647LL) throw RtError{"grid too large", 1};
-    if (smem > 48 * 1024) {
-        static thread_local const void* last = nullptr;
-        static thread_local size_t last_smem = 0;
-        if (last != (const void*)kernel || last_smem < smem) {
-            RT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            last = (const void*)kernel;
-            last_smem = smem;
-        }
-    }
+    // opt in to > 48 KB of dynamic shared memory; set on every such launch (the attribute is per
+    // device and per kernel, a cache keyed on the function type alone would be wrong for both)
+    if (smem > 48 * 1024)
+        RT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kernel<<<(unsigned)grid, block, smem, s>>>(params);
     RT_CUDA(cudaGetLastError());
 }

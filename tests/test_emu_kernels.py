@@ -147,3 +147,41 @@ def test_long_1d_four_step_path(pkg, emu_ctx, monkeypatch, N, like, layout):
     monkeypatch.setenv("MGVIB200_BIG_MIN", "64")
     cfg = _field(pkg, (N,), like, 3, layout)
     assert_field_ops(check_field_ops(pkg, emu_ctx, cfg, check_step=True), cfg)
+
+
+def test_zero_draws_and_single_iteration(pkg, emu_ctx):
+    """gamma = 0 leaves x = 0 without iterating (Krylov.jl: 'x = 0 is a zero-residual solution');
+    maxiters = 1 stops after exactly one update."""
+    cfg = _field(pkg, (16, 16), "LIKE_POISSON", 2)
+    m = pkg.model_from_config(cfg, emu_ctx)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(), emu_ctx)
+    R, info = pkg.sample_residuals(s, 2, draws=(np.zeros_like(cfg["Z1"]), np.zeros_like(cfg["Z2"])), return_info=True)
+    assert np.all(R == 0.0) and info["iters"].tolist() == [0, 0]
+    # one zero right-hand side next to a live one: masks are per vector
+    Z1, Z2 = cfg["Z1"].copy(), cfg["Z2"].copy()
+    Z1[:, 0] = 0.0
+    Z2[:, 0] = 0.0
+    om = oracle_model(cfg)
+    R, info = pkg.sample_residuals(s, 2, draws=(Z1, Z2), return_info=True)
+    Ro, ito, _ = O.sample_residuals_cg(om, cfg["center"], Z1, Z2)
+    assert info["iters"][0] == 0 and np.all(R[:, 0] == 0.0)
+    assert abs(int(info["iters"][1]) - int(ito[1])) <= 2 and rel(R[:, 1], Ro[:, 1]) < 1e-6
+    s1 = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(maxiters=1), emu_ctx)
+    R1, info1 = pkg.sample_residuals(s1, 2, draws=(cfg["Z1"], cfg["Z2"]), return_info=True)
+    Ro1, ito1, _ = O.sample_residuals_cg(om, cfg["center"], cfg["Z1"], cfg["Z2"], itmax=1)
+    assert info1["iters"].tolist() == [1, 1] == ito1.tolist() and rel(R1, Ro1) < RTOL
+    m.close()
+
+
+def test_poisson_identity_link(pkg, emu_ctx):
+    """Poisson rate with the identity link (F = 1/lambda, g' = 1): lambda = c H(A xi) + offset > 0."""
+    syn = pkg.synthetic
+    cfg = syn.field_config((32,), syn.LIKE_POISSON, 2, field_std=0.3, offset=6.0)
+    cfg["link"] = syn.LINK_IDENTITY
+    rate = oracle_model(cfg).rate(cfg["xi_true"])
+    assert rate.min() > 0
+    cfg["data"] = np.random.default_rng(7).poisson(rate).astype(float)
+    cfg["center"] = 0.2 * cfg["center"]
+    assert oracle_model(cfg).rate(cfg["center"]).min() > 0
+    out = check_field_ops(pkg, emu_ctx, cfg, check_step=False)
+    assert_field_ops(out)
