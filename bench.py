@@ -362,10 +362,21 @@ def main():
         k["share"] = k["avg_ms"] * k["launches"] / tot_ms
     kern.sort(key=lambda k: -k["share"])
     dom = kern[0] if kern else None
+    # DRAM bytes per launch of each kernel from the committed `ncu --set full` capture of this same
+    # workload (profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum, 32 samples)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload, {})
+    except Exception:
+        pass
+    for k_ in kern:
+        t_ = traffic.get(str(k_["tag"]))
+        k_["dram_traffic_bytes_per_launch"] = (t_ * n_loc / 32.0) if (t_ and world >= 1) else None
     roofline = None
     if dom and "algorithmic_gbs" in dom:
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["algorithmic_gbs"], "peak": hbm_peak,
-                    "unit": "GB/s", "frac": dom["algorithmic_gbs"] / hbm_peak, "traffic": None,
+                    "unit": "GB/s", "frac": dom["algorithmic_gbs"] / hbm_peak,
+                    "traffic": dom.get("dram_traffic_bytes_per_launch"),
                     "peak_source": peak_src, "share_of_step": dom["share"],
                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"]}
     # the whole Fisher-CG iteration against B_cg: what north_star's 60 % target is about

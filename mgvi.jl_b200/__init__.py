@@ -10,5 +10,5 @@ from .api import (B200CG, B200Dense, B200NewtonCG, CorrelatedFieldModel, DenseLi
                   FullResidualSampler, FwdDerJacobianFunc, FwdRevADJacobianFunc, ImplicitResidualSampler,
                   KrylovJL_CG, MatrixInversion, MGVIConfig, MGVIContext, MGVIResult, NewtonCG, PolynomialModel,
                   ResidualSampler, build_samples, fisher_information, kl_value_grad, mean_metric_apply,
-                  mgvi_kl_optimize_step, mgvi_sample, mgvi_step, model_from_config, newtoncg_optimize,
+                  mgvi_kl_optimize_step, mgvi_mvnormal_pushfwd_function, mgvi_sample, mgvi_step, model_from_config, newtoncg_optimize,
                   sample_residuals)

@@ -493,6 +493,29 @@ def mgvi_sample(forward_model, data, n_residuals: int, center, config: MGVIConfi
     return samples
 
 
+def mgvi_mvnormal_pushfwd_function(forward_model, data, config: MGVIConfig, center_point, context: MGVIContext):
+    """`mgvi_mvnormal_pushfwd_function` (src/mgvi_impl.jl:191-198): a function that pushes standard
+    normal vectors forward to the MGVI posterior approximation, `z -> L_Sigma z + center`
+    (`MulAdd(residual_pushfwd_operator(sampler), center)`).  As in the reference this instantiates
+    the metric densely (MatrixInversion), so it is for low-dimensional models; the product
+    `L_Sigma z` runs on the device."""
+    sampler = ResidualSampler(forward_model, center_point, MatrixInversion(), context)
+    center = sampler.center_point.copy()
+
+    def pushfwd(z):
+        z = as_f64(z)
+        single = z.ndim == 1
+        Z = np.asfortranarray(z.reshape(forward_model.n_theta, -1, order="F"))
+        # the sampler was linearised at `center`; re-linearise if the model has been used elsewhere since
+        context.check(context.lib.linearize(forward_model.handle, ptr(center)))
+        R = np.empty_like(Z, order="F")
+        context.check(context.lib.sample_residuals_dense(forward_model.handle, ptr(Z), Z.shape[1], ptr(R), None))
+        out = center[:, None] + R
+        return out[:, 0] if single else out
+
+    return pushfwd
+
+
 def kl_value_grad(forward_model: _Model, x, R, want_grad: bool = True):
     """`_mean_neg_log_pstr` and its gradient (src/mgvi_impl.jl:19-28, src/newtoncg.jl:100)."""
     m, ctx = forward_model, forward_model.context

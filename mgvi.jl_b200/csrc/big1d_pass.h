@@ -155,7 +155,7 @@ SIMT_DEVICE void big1d_body(const BigParams& B, unsigned char* smem_raw) {
             for (int m = 0; m < 8; ++m) {
                 const int k = lt + m * n8;
                 const int kp = zero_line ? (int)((len - k) & (len - 1)) : (int)(len - 1 - k);
-                const double2 zn = pv.at(kp);
+                const double2 zn = pv.raw(kp);
                 const double2 zk = v[m];
                 v[m] = make_double2(zk.x - zk.y + zn.x + zn.y, zk.x + zk.y + zn.y - zn.x);
             }

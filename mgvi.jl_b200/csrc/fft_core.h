@@ -31,7 +31,14 @@ SIMT_HD double2 cmul(double2 a, double2 b) {
 // multiply by -i
 SIMT_HD double2 cmul_mi(double2 a) { return make_double2(a.y, -a.x); }
 
-SIMT_HD int swz(int chunk) { return chunk ^ ((chunk >> 3) & 7); }
+// XOR swizzle of the 16-byte chunk index (only bits 3..5 are looked at, only bits 0..2 change).
+// One line per unit (lgL = 0): bits 0..2 ^= bits 3..5 (the TMA 128-byte pattern).  Side-by-side
+// lines (lgL >= 1) keep the line index in bit 0, so the row bits are folded into bits 1..2 instead.
+// Checked by simulation of every stage's access pattern (tools/bank_conflicts.py): conflict-free
+// for the benchmark shapes.
+SIMT_HD int swz(int chunk, int lgL) {
+    return lgL == 0 ? (chunk ^ ((chunk >> 3) & 7)) : (chunk ^ ((((chunk >> 3) ^ (chunk >> 4)) << 1) & 7));
+}
 
 // in-place radix-2 butterfly
 SIMT_HD void bfly2(double2& a, double2& b) {
@@ -73,8 +80,11 @@ SIMT_HD void dft8(double2 (&a)[8]) {
 struct LineView {
     double2* sm;     // base of the unit's buffer (L*n chunks)
     int lgL, l;
-    SIMT_DEVICE int idx(int k) const { return swz((k << lgL) | l); }
+    SIMT_DEVICE int idx(int k) const { return swz((k << lgL) | l, lgL); }
     SIMT_DEVICE double2& at(int k) const { return sm[idx(k)]; }
+    // unswizzled position: the final exchange (own outputs out, mirrored partners in) touches runs of
+    // consecutive chunks that straddle 8-chunk blocks, which the swizzle would turn into 2-way conflicts
+    SIMT_DEVICE double2& raw(int k) const { return sm[(k << lgL) | l]; }
 };
 
 // Forward FFT of the line whose elements the calling threads hold in v (v[m] = x[lt + m*n/8]).
@@ -153,13 +163,17 @@ SIMT_DEVICE void fft_line_forward(double2 (&v)[8], const LineView& lv, int lt, i
             const int base = ((lt >> lgNs) << (lgNs + 3)) | jlo;
             const int cb = (base << lgL) | lv.l;
             const int sh = lgNs + lgL;
-            if (sh >= 6) {
-                const int w0 = swz(cb);
+            if (lgNs + 3 >= log2n) {
+                // final stage: plain positions (see LineView::raw)
+#pragma unroll
+                for (int t = 0; t < 8; ++t) lv.sm[cb + (t << sh)] = v[t];
+            } else if (sh >= 6) {
+                const int w0 = swz(cb, lgL);
 #pragma unroll
                 for (int t = 0; t < 8; ++t) lv.sm[w0 + (t << sh)] = v[t];
             } else {
 #pragma unroll
-                for (int t = 0; t < 8; ++t) lv.sm[swz(cb + (t << sh))] = v[t];
+                for (int t = 0; t < 8; ++t) lv.sm[swz(cb + (t << sh), lgL)] = v[t];
             }
         }
         SIMT_SYNC();
@@ -179,9 +193,8 @@ SIMT_DEVICE void dht_combine_read(double2 (&v)[8], const LineView& lv, int lt, i
     const int log2n = LG ? LG : log2n_rt;
     const int n8 = 1 << (log2n - 3);
     const int rd_step = n8 << lv.lgL;
-    const bool rd_fast = (rd_step & 63) == 0;
     const int plt = (n8 - lt) & (n8 - 1);
-    const int p0 = lv.idx(plt);
+    const int p0 = (plt << lv.lgL) | lv.l;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         double2 zn[4];
@@ -189,7 +202,7 @@ SIMT_DEVICE void dht_combine_read(double2 (&v)[8], const LineView& lv, int lt, i
         for (int j = 0; j < 4; ++j) {
             const int m = 4 * h + j;
             const int pm = (lt == 0) ? ((8 - m) & 7) : (7 - m);
-            zn[j] = lv.sm[rd_fast ? p0 + pm * rd_step : lv.idx(plt + pm * n8)];
+            zn[j] = lv.sm[p0 + pm * rd_step];
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {

@@ -87,7 +87,26 @@ SIMT_DEVICE void vec_body(const VecParams& P, unsigned char* smem_raw) {
     long long hi = lo + P.per_block;
     if (hi > P.N) hi = P.N;
     double acc = 0.0;
-    for (long long i = lo + SIMT_TID; i < hi; i += SIMT_NTID) vec_elem(P, s, i, alpha, acc);
+    if (P.op == VOP_CG_UPDATE && (P.N & 1) == 0) {
+        // the streaming update of the CG iteration moves 48 bytes per element: 16-byte accesses,
+        // all loads of a pair issued before its stores
+        const long long base = (long long)s * P.N;
+        const double2* __restrict__ p2 = reinterpret_cast<const double2*>(P.p + base);
+        const double2* __restrict__ a2 = reinterpret_cast<const double2*>(P.Ap + base);
+        double2* __restrict__ x2 = reinterpret_cast<double2*>(P.x + base);
+        double2* __restrict__ r2 = reinterpret_cast<double2*>(P.r + base);
+        for (long long i = (lo >> 1) + SIMT_TID; i < (hi >> 1); i += SIMT_NTID) {
+            const double2 pv = p2[i], av = a2[i];
+            double2 xv = x2[i], rv = r2[i];
+            xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+            rv.x -= alpha * av.x; rv.y -= alpha * av.y;
+            x2[i] = xv; r2[i] = rv;
+            acc += rv.x * rv.x;
+            acc += rv.y * rv.y;
+        }
+    } else {
+        for (long long i = lo + SIMT_TID; i < hi; i += SIMT_NTID) vec_elem(P, s, i, alpha, acc);
+    }
     if (P.fin == FIN_NONE) return;
     const double tot = seg_reduce(acc, SIMT_NTID, red);
     if (P.fin == FIN_TOTAL)

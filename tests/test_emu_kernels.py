@@ -185,3 +185,17 @@ def test_poisson_identity_link(pkg, emu_ctx):
     assert oracle_model(cfg).rate(cfg["center"]).min() > 0
     out = check_field_ops(pkg, emu_ctx, cfg, check_step=False)
     assert_field_ops(out)
+
+
+def test_mvnormal_pushfwd_function(pkg, emu_ctx):
+    """`mgvi_mvnormal_pushfwd_function` (src/mgvi_impl.jl:191-198): z -> L_Sigma z + center."""
+    cfg = pkg.synthetic.polyfit_config(2, reference_grid=True)
+    m = pkg.model_from_config(cfg, emu_ctx)
+    c = cfg["true_params"]
+    f = pkg.mgvi_mvnormal_pushfwd_function(m, cfg["data"], pkg.MGVIConfig(), c, emu_ctx)
+    L = O.residual_pushfwd_operator(oracle_model(cfg), c)
+    z = np.random.default_rng(3).standard_normal(5)
+    assert rel(f(z), L @ z + c) < 1e-9
+    Z = np.random.default_rng(4).standard_normal((5, 3))
+    assert rel(f(Z), L @ Z + c[:, None]) < 1e-9
+    m.close()
