@@ -47,6 +47,7 @@ struct FieldEngine : Engine {
     int prefetch_waves = 0;     // software L2 prefetch distance in resident-block waves (0 = off: measured slower at C3, profiles/README.md)
     bool use_hot = true;        // compile-time-shape kernels for the benchmark sizes
     int prefetch_epi = 0;       // L1 hints for post-transform operands (MGVIB200_PREFETCH_EPI)
+    int stage_vin = 1;          // TMA bulk staging of the '+ v' rows in the hot last pass (MGVIB200_STAGE_VIN)
 
     DevBuf A, data, w, q, wbar, center;
     std::map<long long, DevBuf> tw, cas;
@@ -110,6 +111,7 @@ struct FieldEngine : Engine {
         if (const char* e = getenv("MGVIB200_PREFETCH_WAVES")) prefetch_waves = std::max(0, atoi(e));
         if (const char* e = getenv("MGVIB200_NO_HOT")) use_hot = !atoi(e);
         if (const char* e = getenv("MGVIB200_PREFETCH_EPI")) prefetch_epi = atoi(e);
+        if (const char* e = getenv("MGVIB200_STAGE_VIN")) stage_vin = atoi(e);
         if (getenv("MGVIB200_FORCE_GENERIC") && atoi(getenv("MGVIB200_FORCE_GENERIC"))) big = false;
         if (!fast)
             for (int i = 0; i < ndim; ++i)
@@ -305,7 +307,14 @@ struct FieldEngine : Engine {
 
     // compile-time-shape build; the block size follows from (LG, LGL): 2^(LG - 3 + LGL) threads per unit
     template <int GEO, int PRO, int EPI, bool DBL, int LG, int LGL>
-    void launch_hot(const FieldPassParams& P, const PassGeo& g, long long grid) {
+    void launch_hot(const FieldPassParams& P0, const PassGeo& g0, long long grid) {
+        FieldPassParams P = P0;
+        PassGeo g = g0;
+        if (GEO == GEO_CONTIG && EPI == EPI_METRIC && stage_vin && P.vin != P.out &&
+            field_pass_smem_bytes_staged(g.n, g.L, g.G) <= 72 * 1024) {
+            P.stage_vin = 1;
+            g.smem = (size_t)field_pass_smem_bytes_staged(g.n, g.L, g.G);
+        }
         constexpr int upt = (LG > 0) ? (1 << (LG - 3 + LGL)) : 256;
         if (upt <= 256)
             rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 256, MGVI_MINB, LG, LGL, false>, grid, g.threads, g.smem, ctx->stream, P);

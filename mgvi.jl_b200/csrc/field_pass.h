@@ -70,6 +70,7 @@ struct FieldPassParams {
     int mask_active;                          // skip vectors whose cg.active flag is 0 (CG iterations only)
     int prefetch_blocks;                      // > 0: hint the inputs of block (this + prefetch_blocks) into L2
     int prefetch_epi;                         // hint the epilogue / mid operands into L1 before the transform
+    int stage_vin;                            // contiguous EPI_METRIC: TMA-stage the '+ v' rows into shared memory at block start
     // ---- reduction ------------------------------------------------------------------------
     int fin;
     double* partials; unsigned* counters; double* red_out;
@@ -255,6 +256,33 @@ SIMT_DEVICE void pro_cg_block(double2 (&v)[8], double* __restrict__ p, const dou
     }
 }
 
+// same as epi_metric_block below, with the '+ v' rows already in shared memory (row a at stg[0..n),
+// row b at stg[n..2n)); contiguous geometry only
+SIMT_DEVICE void epi_metric_block_staged(const double2 (&v)[8], double* __restrict__ out, const double* stg,
+                                         const double* __restrict__ A, unsigned off_a, unsigned off_b, unsigned step,
+                                         long long out_off, int lt, int n, double scale, double& acc) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        double2 vi[4], aa[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = lt + (4 * h + j) * (int)step;
+            const unsigned oa = off_a + (4 * h + j) * step, ob = off_b + (4 * h + j) * step;
+            vi[j] = make_double2(stg[k], stg[n + k]);
+            aa[j] = ld_pair(A, oa, ob, true, true, false);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned oa = off_a + (4 * h + j) * step, ob = off_b + (4 * h + j) * step;
+            const double2 val = v[4 * h + j];
+            const double2 o = make_double2(vi[j].x + scale * (aa[j].x * val.x), vi[j].y + scale * (aa[j].y * val.y));
+            st_pair(out, out_off + oa, out_off + ob, true, true, false, o);
+            acc += vi[j].x * o.x;
+            acc += vi[j].y * o.y;
+        }
+    }
+}
+
 template <bool ADJ>
 SIMT_DEVICE void epi_metric_block(const double2 (&v)[8], double* __restrict__ out, const double* __restrict__ vin,
                                   const double* __restrict__ A, unsigned off_a, unsigned off_b, unsigned step,
@@ -392,6 +420,10 @@ static const int kSmemHeader = 512;
 SIMT_HD long long field_pass_smem_bytes(int n, int L, int G) {
     return kSmemHeader + (long long)G * L * n * 16;
 }
+// with the TMA-staged '+ v' operand: one row pair (2n doubles) per unit behind the FFT buffers
+SIMT_HD long long field_pass_smem_bytes_staged(int n, int L, int G) {
+    return field_pass_smem_bytes(n, L, G) + (long long)G * 2 * n * 8;
+}
 
 // GEO is a compile-time geometry class:
 //   GEO_CONTIG : lines along the last (contiguous) axis; a unit = two neighbouring rows of one vector
@@ -523,6 +555,21 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
 #pragma unroll
             for (int m = 0; m < 8; ++m) v[m] = make_double2(0.0, 0.0);
         }
+        // TMA staging of the '+ v' rows (contiguous last pass): the row pair is one contiguous chunk of 2n
+        // doubles; one thread arms an mbarrier and issues a bulk copy (UBLKCP) that lands while the
+        // transform runs -- the epilogue then reads shared memory instead of stalling on a second
+        // global load phase
+        double* stg = nullptr;
+        unsigned long long* mbar = nullptr;
+        const bool staged = (EPI == EPI_METRIC) && (GEO == GEO_CONTIG) && !LOOP && (P.stage_vin != 0);
+        if (staged) {
+            stg = reinterpret_cast<double*>(smem_raw + kSmemHeader + ((long long)P.G << (lgL + log2n + 4))) + ((long long)g << (log2n + 1));
+            mbar = reinterpret_cast<unsigned long long*>(smem_raw + 264) + g;
+            if (tu == 0 && valid) {
+                SIMT_MBAR_INIT(mbar, 1);
+                SIMT_BULK_G2S(stg, P.vin + (long long)sa * P.vin_ld + (off_a - lt), 16u << log2n, mbar);
+            }
+        }
         // operands only needed AFTER the transform (the "+ v" term, the mid weight): start them towards
         // L1 now -- a hint costs no register and no scoreboard entry, the later load then hits
         if (P.prefetch_epi && valid && !pairvec) {
@@ -572,6 +619,10 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
 #pragma unroll
                 for (int m = 0; m < 8; ++m)
                     epi_pair<EPI>(P, sa, sb, off_a + m * step, off_b + m * step, va, vb, false, v[m], acc_a, acc_b, accv[m]);
+            } else if (EPI == EPI_METRIC && staged) {
+                SIMT_MBAR_WAIT(mbar, 0);
+                epi_metric_block_staged(v, P.out, stg, P.A, off_a, off_b, step, (long long)sa * P.out_ld, lt, 1 << log2n,
+                                        P.scale, acc_a);
             } else if (EPI == EPI_METRIC) {
                 epi_metric_block<GEO == GEO_STRIDED>(v, P.out, P.vin, P.A, off_a, off_b, step, (long long)sa * P.out_ld,
                                                      (long long)sa * P.vin_ld, P.scale, acc_a);

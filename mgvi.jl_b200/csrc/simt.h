@@ -31,6 +31,23 @@
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"((unsigned)(bytes)) : "memory")
 #define SIMT_PREFETCH_L2(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))
 #define SIMT_PREFETCH_L1(ptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr))
+// TMA bulk copy global -> shared with mbarrier completion (SASS UBLKCP): one thread arms the barrier
+// with the byte count and issues the copy; consumers wait on the barrier phase.  No registers, no LSU.
+#define SIMT_MBAR_INIT(mbar, count)                                                                 \
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n\tfence.mbarrier_init.release.cluster;\n\t" \
+                 "fence.proxy.async.shared::cta;" ::"r"((unsigned)__cvta_generic_to_shared(mbar)), "r"((unsigned)(count)) : "memory")
+#define SIMT_BULK_G2S(dst, src, bytes, mbar)                                                        \
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"                        \
+                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %1, [%0];" \
+                 ::"r"((unsigned)__cvta_generic_to_shared(mbar)), "r"((unsigned)(bytes)),            \
+                   "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory")
+#define SIMT_MBAR_WAIT(mbar, parity)                                                                \
+    do {                                                                                            \
+        unsigned done_ = 0;                                                                         \
+        while (!done_)                                                                              \
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" \
+                         : "=r"(done_) : "r"((unsigned)__cvta_generic_to_shared(mbar)), "r"((unsigned)(parity)) : "memory"); \
+    } while (0)
 // optimisation fence on a 32-bit value: stops the compiler from precomputing (and spilling) the
 // addresses of a later phase at the top of the kernel
 #define SIMT_OPAQUE_U32(x) asm volatile("" : "+r"(x))
@@ -62,6 +79,9 @@
 #define SIMT_PREFETCH_L2(ptr) ((void)0)
 #define SIMT_PREFETCH_L1(ptr) ((void)0)
 #define SIMT_OPAQUE_U32(x) ((void)0)
+#define SIMT_MBAR_INIT(mbar, count) ((void)0)
+#define SIMT_BULK_G2S(dst, src, bytes, mbar) memcpy((dst), (src), (bytes))
+#define SIMT_MBAR_WAIT(mbar, parity) ((void)0)
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
