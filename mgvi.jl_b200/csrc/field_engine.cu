@@ -43,11 +43,11 @@ struct FieldEngine : Engine {
     int link = LINK_EXP, like = LIKE_POISSON, layout = 0;
     long long z1_ld = 0, z1_stride = 1;
     double const_term = 0.0;    // per-point constants of -loglike and of the prior
-    int max_L = 2;              // complex columns per strided tile (2: 512-thread blocks, 2 per SM; measured best at C3)
+    int max_L = 0;              // complex columns per strided tile; 0 = by axis length (strided_L), MGVIB200_STRIDED_L overrides
     int prefetch_waves = 0;     // software L2 prefetch distance in resident-block waves (0 = off: measured slower at C3, profiles/README.md)
     bool use_hot = true;        // compile-time-shape kernels for the benchmark sizes
     int prefetch_epi = 0;       // L1 hints for post-transform operands (MGVIB200_PREFETCH_EPI)
-    int stage_vin = 1;          // TMA bulk staging of the '+ v' rows in the hot last pass (MGVIB200_STAGE_VIN)
+    int stage_vin = 0;          // TMA bulk staging of the '+ v' rows in the hot last pass (needs -DMGVI_STAGE_VIN; MGVIB200_STAGE_VIN=1)
 
     DevBuf A, data, w, q, wbar, center;
     std::map<long long, DevBuf> tw, cas;
@@ -274,7 +274,11 @@ struct FieldEngine : Engine {
             g.ntb = (g.units_per_vec + G - 1) / G;
         } else {
             g.geo = GEO_STRIDED;
-            long long L = std::min<long long>(max_L, g.inner / 2);
+            // tile width by axis length: wide enough that a unit is 256..512 threads, at most 8 complex
+            // columns (a full 128-byte line per row); 2048-point axes: 2 columns (measured best at C3),
+            // 256-point axes: 8 columns (C5)
+            long long Lw = max_L > 0 ? max_L : std::min<long long>(8, std::max<long long>(2, 4096 / g.n));
+            long long L = std::min<long long>(Lw, g.inner / 2);
             while (L * tpl > 1024) L >>= 1;
             while (kSmemHeader + L * g.n * 16 > 220 * 1024) L >>= 1;
             if (L < 1) L = 1;
@@ -310,11 +314,13 @@ struct FieldEngine : Engine {
     void launch_hot(const FieldPassParams& P0, const PassGeo& g0, long long grid) {
         FieldPassParams P = P0;
         PassGeo g = g0;
+#ifdef MGVI_STAGE_VIN
         if (GEO == GEO_CONTIG && EPI == EPI_METRIC && stage_vin && P.vin != P.out &&
             field_pass_smem_bytes_staged(g.n, g.L, g.G) <= 72 * 1024) {
             P.stage_vin = 1;
             g.smem = (size_t)field_pass_smem_bytes_staged(g.n, g.L, g.G);
         }
+#endif
         constexpr int upt = (LG > 0) ? (1 << (LG - 3 + LGL)) : 256;
         if (upt <= 256)
             rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 256, MGVI_MINB, LG, LGL, false>, grid, g.threads, g.smem, ctx->stream, P);
@@ -362,6 +368,7 @@ struct FieldEngine : Engine {
             else if (hot_c && g.log2n == 8) { launch_hot<GEO, PRO, EPI, DBL, hot_c ? 8 : 0, 0>(P, g, grid); done = true; }
             else if (hot_s && DBL && g.log2n == 11 && g.lgL == 2) { launch_hot<GEO, PRO, EPI, DBL, (hot_s && DBL) ? 11 : 0, 2>(P, g, grid); done = true; }
             else if (hot_s && DBL && g.log2n == 11 && g.lgL == 1) { launch_hot<GEO, PRO, EPI, DBL, (hot_s && DBL) ? 11 : 0, 1>(P, g, grid); done = true; }
+            else if (hot_s && g.log2n == 8 && g.lgL == 3) { launch_hot<GEO, PRO, EPI, DBL, hot_s ? 8 : 0, 3>(P, g, grid); done = true; }
             else if (hot_s && g.log2n == 8 && g.lgL == 2) { launch_hot<GEO, PRO, EPI, DBL, hot_s ? 8 : 0, 2>(P, g, grid); done = true; }
         }
         if (!done) launch_lg<GEO, PRO, EPI, DBL>(P, g, grid);

@@ -561,7 +561,14 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
         // global load phase
         double* stg = nullptr;
         unsigned long long* mbar = nullptr;
+#ifdef MGVI_STAGE_VIN
         const bool staged = (EPI == EPI_METRIC) && (GEO == GEO_CONTIG) && !LOOP && (P.stage_vin != 0);
+#else
+        // measured on B200 (profiles/README.md, v6): 0.771 ms staged vs 0.690 ms unstaged for the C3 last
+        // pass -- the extra 32 KB of shared memory per block shrinks L1 under the twiddle / A reads and
+        // the early copy competes with the primary loads; compiled out unless -DMGVI_STAGE_VIN
+        const bool staged = false;
+#endif
         if (staged) {
             stg = reinterpret_cast<double*>(smem_raw + kSmemHeader + ((long long)P.G << (lgL + log2n + 4))) + ((long long)g << (log2n + 1));
             mbar = reinterpret_cast<unsigned long long*>(smem_raw + 264) + g;

@@ -41,12 +41,29 @@ def test_metric_1d_all_radix_leads(pkg, emu_ctx, n):
     ((8, 16, 8), "LIKE_POISSON", None),
     ((8, 256), "LIKE_POISSON", None),   # 256-point rows: compile-time-length kernels (contiguous)
     ((256, 8), "LIKE_NORMAL", 0),       # 256-point columns: compile-time-length kernels (strided, fused)
+    ((256, 16), "LIKE_POISSON", None),  # ... with the 8-column tile the 256^3 workload uses
     ((40,), "LIKE_NORMAL", 2),          # the reference fixture's length: generic (non power of two) path
     ((6, 10), "LIKE_POISSON", None),
 ])
 def test_field_ops_vs_oracle(pkg, emu_ctx, dims, like, layout):
     cfg = _field(pkg, dims, like, 3 if len(dims) == 1 else 2, layout)
     assert_field_ops(check_field_ops(pkg, emu_ctx, cfg, check_step=True), cfg)
+
+
+def test_metric_3d_wide_tiles(pkg, emu_ctx):
+    """3-D field with a 256-point middle axis: the single strided pass with the 8-column tile (the
+    256^3 workload's shape class) plus the fused axis-0 pass; metric product only (an emulated CG
+    solve at this size takes minutes)."""
+    from helpers import oracle_model, rel
+    cfg = _field(pkg, (2, 256, 16), "LIKE_POISSON", 2, None)
+    m = pkg.model_from_config(cfg, emu_ctx)
+    om = oracle_model(cfg)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(), emu_ctx)
+    V = np.random.default_rng(11).standard_normal((m.n_theta, 2))
+    lin = om.linearize(cfg["center"])
+    MVo = np.stack([O.metric_apply(lin, V[:, i]) for i in range(2)], axis=1)
+    assert rel(s.metric_apply(V), MVo) < 1e-12
+    m.close()
 
 
 def test_identity_link_and_normal(pkg, emu_ctx):

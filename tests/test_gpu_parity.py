@@ -49,6 +49,7 @@ def test_metric_1d_every_length(pkg, gpu_ctx, n):
     ((8, 4096), "LIKE_POISSON", None, 2),   # 512-thread row blocks
     ((4096, 16), "LIKE_NORMAL", 0, 2),      # 1024-thread column tiles
     ((256, 256, 8), "LIKE_POISSON", None, 2),   # 3-D with 256-point axes: compile-time-length strided kernels
+    ((16, 256, 16), "LIKE_NORMAL", 0, 2),       # ... with the 8-column tile of the 256^3 workload
     ((32, 64, 16), "LIKE_POISSON", None, 3),
     ((16, 8, 128), "LIKE_NORMAL", 0, 2),
     ((40,), "LIKE_NORMAL", 2, 4),          # reference fixture length, generic path
