@@ -338,7 +338,8 @@ int mgvib200_metric_apply_dev(mgvib200_model* m, const double* V, int64_t k, dou
     if (!m) return MGVIB200_ERR_INVALID;
     return guarded(m->ctx, [&] {
         need(m->linearized, "metric_apply: call mgvib200_linearize first");
-        need(k >= 1, "metric_apply: k must be >= 1");
+        need(k >= 0, "metric_apply: k must be >= 0");
+        if (k == 0) return;     // empty batch: nothing to do (the reference returns an n_theta x 0 matrix)
         rt_set_device(m->ctx->device);
         m->eng->metric_apply(V, k, MV);
         rt_sync(m->ctx->stream);
@@ -351,7 +352,8 @@ int mgvib200_sample_residuals_cg_dev(mgvib200_model* m, const double* Z1, const 
     if (!m) return MGVIB200_ERR_INVALID;
     return guarded(m->ctx, [&] {
         need(m->linearized, "sample_residuals_cg: call mgvib200_linearize first");
-        need(n >= 1, "sample_residuals_cg: n must be >= 1");
+        need(n >= 0, "sample_residuals_cg: n must be >= 0");
+        if (n == 0) return;     // empty batch: nothing to do (the reference returns an n_theta x 0 matrix)
         rt_set_device(m->ctx->device);
         m->eng->sample_cg(Z1, Z2, n, cg_defaults(opts), R, iters_host, rnorm_host);
     });
@@ -394,7 +396,8 @@ int mgvib200_metric_apply(mgvib200_model* m, const double* V, int64_t k, double*
     if (!m || !V || !MV) return MGVIB200_ERR_INVALID;
     return guarded(m->ctx, [&] {
         need(m->linearized, "metric_apply: call mgvib200_linearize first");
-        need(k >= 1, "metric_apply: k must be >= 1");
+        need(k >= 0, "metric_apply: k must be >= 0");
+        if (k == 0) return;     // empty batch: nothing to do (the reference returns an n_theta x 0 matrix)
         rt_set_device(m->ctx->device);
         const size_t cnt = (size_t)m->eng->n_theta * k;
         double* v = stage_in(m, 1, V, cnt);
@@ -410,7 +413,8 @@ int mgvib200_sample_residuals_cg(mgvib200_model* m, const double* Z1, const doub
     if (!m || !Z1 || !Z2 || !R) return MGVIB200_ERR_INVALID;
     return guarded(m->ctx, [&] {
         need(m->linearized, "sample_residuals_cg: call mgvib200_linearize first");
-        need(n >= 1, "sample_residuals_cg: n must be >= 1");
+        need(n >= 0, "sample_residuals_cg: n must be >= 0");
+        if (n == 0) return;     // empty batch: nothing to do (the reference returns an n_theta x 0 matrix)
         rt_set_device(m->ctx->device);
         double* z1 = stage_in(m, 1, Z1, (size_t)m->eng->n_lambda * n);
         double* z2 = stage_in(m, 2, Z2, (size_t)m->eng->n_theta * n);
@@ -425,7 +429,8 @@ int mgvib200_sample_residuals_dense(mgvib200_model* m, const double* Z, int64_t 
     if (!m || !Z || !R) return MGVIB200_ERR_INVALID;
     return guarded(m->ctx, [&] {
         need(m->linearized, "sample_residuals_dense: call mgvib200_linearize first");
-        need(n >= 1, "sample_residuals_dense: n must be >= 1");
+        need(n >= 0, "sample_residuals_dense: n must be >= 0");
+        if (n == 0) return;     // empty batch: nothing to do (the reference returns an n_theta x 0 matrix)
         rt_set_device(m->ctx->device);
         const size_t nt = (size_t)m->eng->n_theta;
         double* z = stage_in(m, 1, Z, nt * n);
@@ -490,7 +495,8 @@ int mgvib200_newtoncg(mgvib200_model* m, const double* x0, const double* R, int6
 int mgvib200_build_samples(mgvib200_model* m, const double* center, const double* R, int64_t n, double* samples) {
     if (!m || !center || !R || !samples) return MGVIB200_ERR_INVALID;
     return guarded(m->ctx, [&] {
-        need(n >= 1, "build_samples: n must be >= 1");
+        need(n >= 0, "build_samples: n must be >= 0");
+        if (n == 0) return;     // empty batch: nothing to do (the reference returns an n_theta x 0 matrix)
         rt_set_device(m->ctx->device);
         const size_t nt = (size_t)m->eng->n_theta;
         double* cd = stage_in(m, 0, center, nt);

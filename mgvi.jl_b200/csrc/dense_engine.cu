@@ -30,83 +30,127 @@ struct TriParams {
 };
 enum { TRI_POTRF = 0, TRI_PANEL = 1, TRI_BACK = 2, TRI_SYM = 3, TRI_EYE = 4 };
 
-// TRI_POTRF: upper Cholesky of the diagonal block in place (one block).
+// TRI_POTRF: upper Cholesky of the diagonal block in place (one block of 256 threads).
 // TRI_PANEL: X = R_jj^-T A_panel for columns c0.. of block row j0 (thread per column), in place.
 // TRI_BACK : Y = R_jj^-1 W for rows j0..j0+nb of X (thread per column), in place.
 // TRI_SYM  : mirror the upper triangle into the lower one.   TRI_EYE: A = identity.
-SIMT_DEVICE void tri_body(const TriParams& P, unsigned char* smem) {
-    double* S = reinterpret_cast<double*>(smem);          // [nb][nb + 1]
-    const int nb = P.nb, lds = nb + 1, tid = SIMT_TID, nt = SIMT_NTID;
-    if (P.mode == TRI_SYM || P.mode == TRI_EYE) {
-        const long long total = (long long)P.n * P.n;
-        for (long long idx = SIMT_BID * nt + tid; idx < total; idx += SIMT_NBID * nt) {
-            const long long r = idx % P.n, c = idx / P.n;
-            if (P.mode == TRI_EYE) P.A[r + c * P.ld] = (r == c) ? 1.0 : 0.0;
-            else if (r > c) P.A[r + c * P.ld] = P.A[c + r * P.ld];
-        }
-        return;
-    }
-    // diagonal block -> shared (S[row][col])
-    for (int idx = tid; idx < nb * nb; idx += nt) {
-        const int r = idx % nb, c = idx / nb;
-        S[r * lds + c] = P.A[(P.j0 + r) + (long long)(P.j0 + c) * P.ld];
-    }
-    SIMT_SYNC();
-    if (P.mode == TRI_POTRF) {
-        for (int j = 0; j < nb; ++j) {
-            if (tid == 0) S[j * lds + j] = sqrt(S[j * lds + j]);
-            SIMT_SYNC();
-            const double d = S[j * lds + j];
-            for (int c = j + 1 + tid; c < nb; c += nt) S[j * lds + c] /= d;
-            SIMT_SYNC();
-            // trailing update of the upper triangle: S[a][b] -= R[j][a] R[j][b], j < a <= b
-            const int rem = nb - j - 1;
-            for (int idx = tid; idx < rem * rem; idx += nt) {
-                const int a = j + 1 + idx / rem, b = j + 1 + idx % rem;
-                if (a <= b) S[a * lds + b] -= S[j * lds + a] * S[j * lds + b];
-            }
-            SIMT_SYNC();
-        }
-        for (int idx = tid; idx < nb * nb; idx += nt) {
-            const int r = idx % nb, c = idx / nb;
-            P.A[(P.j0 + r) + (long long)(P.j0 + c) * P.ld] = (r <= c) ? S[r * lds + c] : 0.0;
-        }
-        return;
-    }
-    // column tile -> shared T[i][tid] (after S)
-    double* T = S + nb * lds;
-    const int ncol_blk = nt;
-    const long long cbase = P.c0 + SIMT_BID * ncol_blk;
-    for (int idx = tid; idx < nb * ncol_blk; idx += nt) {
-        const int i = idx % nb, c = idx / nb;
-        if (cbase + c < P.c0 + P.ncols) T[i * ncol_blk + c] = P.X[(P.j0 + i) + (cbase + c) * P.ldx];
-    }
-    SIMT_SYNC();
-    if (cbase + tid < P.c0 + P.ncols) {
-        if (P.mode == TRI_PANEL) {
-            // solve R_jj' x = a : x_i = (a_i - sum_{l<i} R[l][i] x_l) / R[i][i]
-            for (int i = 0; i < nb; ++i) {
-                double acc = T[i * ncol_blk + tid];
-                for (int l = 0; l < i; ++l) acc -= S[l * lds + i] * T[l * ncol_blk + tid];
-                T[i * ncol_blk + tid] = acc / S[i * lds + i];
-            }
-        } else {
-            // solve R_jj y = w : y_i = (w_i - sum_{l>i} R[i][l] y_l) / R[i][i]
-            for (int i = nb - 1; i >= 0; --i) {
-                double acc = T[i * ncol_blk + tid];
-                for (int l = i + 1; l < nb; ++l) acc -= S[i * lds + l] * T[l * ncol_blk + tid];
-                T[i * ncol_blk + tid] = acc / S[i * lds + i];
-            }
-        }
-    }
-    SIMT_SYNC();
-    for (int idx = tid; idx < nb * ncol_blk; idx += nt) {
-        const int i = idx % nb, c = idx / nb;
-        if (cbase + c < P.c0 + P.ncols) P.X[(P.j0 + i) + (cbase + c) * P.ldx] = T[i * ncol_blk + c];
+//
+// All three block kernels work on a full kNb x kNb block held in registers; a short last block
+// (nb < kNb) is padded with the identity, which the factorisation and both solves leave alone.
+SIMT_DEVICE void tri_fill_body(const TriParams& P) {
+    const long long total = (long long)P.n * P.n;
+    const int tid = SIMT_TID, nt = SIMT_NTID;
+    for (long long idx = SIMT_BID * nt + tid; idx < total; idx += SIMT_NBID * nt) {
+        const long long r = idx % P.n, c = idx / P.n;
+        if (P.mode == TRI_EYE) P.A[r + c * P.ld] = (r == c) ? 1.0 : 0.0;
+        else if (r > c) P.A[r + c * P.ld] = P.A[c + r * P.ld];
     }
 }
 
-SIMT_GLOBAL(128) k_tri(SIMT_KARGS(TriParams)) { SIMT_SMEM_DECL tri_body(P, simt_smem); }
+// diagonal block -> shared S[row * lds + col], identity-padded to kNb x kNb
+SIMT_DEVICE void tri_load_diag(const TriParams& P, double* S, int lds) {
+    const int nb = P.nb, tid = SIMT_TID, nt = SIMT_NTID;
+    for (int idx = tid; idx < kNb * kNb; idx += nt) {
+        const int r = idx % kNb, c = idx / kNb;
+        S[r * lds + c] = (r < nb && c < nb) ? P.A[(P.j0 + r) + (long long)(P.j0 + c) * P.ld] : (r == c ? 1.0 : 0.0);
+    }
+}
+
+// Right-looking Cholesky of one kNb x kNb block, 256 threads.  Thread (g = tid / 64, b = tid % 64)
+// keeps the 16 elements S[4 i + g][b] in registers; per column j: the 64 owners of row j publish
+// it, 64 threads scale it (R[j][c] = S[j][c] / sqrt(S[j][j])), everyone applies the rank-1 update
+// to its registers.  Two barriers per column, no shared-memory traffic for the trailing block.
+SIMT_DEVICE void potrf_body(const TriParams& P, unsigned char* smem) {
+    constexpr int lds = kNb + 1;
+    double* S = reinterpret_cast<double*>(smem);          // [kNb][kNb + 1]: input block, then the factor
+    double* rowbuf = S + kNb * lds;                       // [2][kNb] unscaled pivot row, double-buffered
+    const int tid = SIMT_TID, g = tid >> 6, b = tid & 63;
+    tri_load_diag(P, S, lds);
+    SIMT_SYNC();
+    double reg[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) reg[i] = S[(4 * i + g) * lds + b];
+    SIMT_SYNC();
+    for (int j = 0; j < kNb; ++j) {
+        double* rb_ = rowbuf + (j & 1) * kNb;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (4 * i + g == j) rb_[b] = reg[i];
+        SIMT_SYNC();
+        // every thread scales by 1 / sqrt(pivot) itself (as LAPACK's dpotf2 scales by the reciprocal):
+        // one barrier per column, no serial divide behind the square root
+        const double rinv = SIMT_RSQRT(rb_[j]);
+        const double rb = rb_[b] * rinv;
+        if (g == 0) S[j * lds + b] = (b >= j) ? rb : 0.0;  // row j of R
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int a = 4 * i + g;
+            if (a > j && a <= b) reg[i] -= (rb_[a] * rinv) * rb;
+        }
+    }
+    SIMT_SYNC();
+    for (int idx = tid; idx < kNb * kNb; idx += SIMT_NTID) {
+        const int r = idx % kNb, c = idx / kNb;
+        if (r < P.nb && c < P.nb) P.A[(P.j0 + r) + (long long)(P.j0 + c) * P.ld] = S[r * lds + c];
+    }
+}
+
+// Triangular solves with the diagonal block, one right-hand-side column per thread held in 64
+// registers (right-looking substitution: every update of a step is independent, so the FP64 pipe
+// sees 63, 62, ... independent FMAs instead of one dependent chain per row).
+static const int kTriCols = 64;       // columns (threads) per block of the solve kernel
+SIMT_DEVICE void trsolve_body(const TriParams& P, unsigned char* smem) {
+    constexpr int lds = kNb + 1;
+    double* S = reinterpret_cast<double*>(smem);          // [kNb][kNb + 1]
+    double* T = S + kNb * lds;                            // [kNb][kTriCols] staging of the column tile
+    const int tid = SIMT_TID, nt = SIMT_NTID;
+    tri_load_diag(P, S, lds);
+    const long long cbase = P.c0 + SIMT_BID * (long long)kTriCols;
+    const long long cend = (long long)P.c0 + P.ncols;
+    for (int idx = tid; idx < kNb * kTriCols; idx += nt) {
+        const int i = idx % kNb, c = idx / kNb;
+        T[i * kTriCols + c] = (i < P.nb && cbase + c < cend) ? P.X[(P.j0 + i) + (cbase + c) * P.ldx] : 0.0;
+    }
+    SIMT_SYNC();
+    // reciprocal of the diagonal once (64 parallel divisions) instead of a divide on the critical path
+    // of every substitution step
+    double* dinv = T + kNb * kTriCols;
+    if (tid < kNb) dinv[tid] = 1.0 / S[tid * lds + tid];
+    double t[kNb];
+#pragma unroll
+    for (int i = 0; i < kNb; ++i) t[i] = T[i * kTriCols + tid];
+    SIMT_SYNC();
+    if (P.mode == TRI_PANEL) {
+        // R' x = a:  x_i = a_i / R[i][i], then a_l -= R[i][l] x_i for l > i
+#pragma unroll
+        for (int i = 0; i < kNb; ++i) {
+            const double x = t[i] * dinv[i];
+            t[i] = x;
+#pragma unroll
+            for (int l = i + 1; l < kNb; ++l) t[l] -= S[i * lds + l] * x;
+        }
+    } else {
+        // R y = w:  y_i = w_i / R[i][i] from the bottom, then w_l -= R[l][i] y_i for l < i
+#pragma unroll
+        for (int i = kNb - 1; i >= 0; --i) {
+            const double y = t[i] * dinv[i];
+            t[i] = y;
+#pragma unroll
+            for (int l = 0; l < i; ++l) t[l] -= S[l * lds + i] * y;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kNb; ++i) T[i * kTriCols + tid] = t[i];
+    SIMT_SYNC();
+    for (int idx = tid; idx < kNb * kTriCols; idx += nt) {
+        const int i = idx % kNb, c = idx / kNb;
+        if (i < P.nb && cbase + c < cend) P.X[(P.j0 + i) + (cbase + c) * P.ldx] = T[i * kTriCols + c];
+    }
+}
+
+SIMT_GLOBAL(128) k_tri_fill(SIMT_KARGS(TriParams)) { SIMT_SMEM_DECL (void)simt_smem; tri_fill_body(P); }
+SIMT_GLOBAL(256) k_potrf(SIMT_KARGS(TriParams)) { SIMT_SMEM_DECL potrf_body(P, simt_smem); }
+SIMT_GLOBAL(64) k_trsolve(SIMT_KARGS(TriParams)) { SIMT_SMEM_DECL trsolve_body(P, simt_smem); }
 
 namespace {
 
@@ -144,13 +188,16 @@ struct DenseEngine : Engine {
     void tri(int mode, double* A, long long ld, double* X, long long ldx, int j0, int nb, int c0, int ncols, int n) {
         TriParams t;
         t.A = A; t.ld = ld; t.X = X; t.ldx = ldx; t.j0 = j0; t.nb = nb; t.c0 = c0; t.ncols = ncols; t.mode = mode; t.n = n;
-        long long grid = 1;
-        if (mode == TRI_PANEL || mode == TRI_BACK) grid = (ncols + 127) / 128;
-        if (mode == TRI_SYM || mode == TRI_EYE) grid = std::min<long long>(((long long)n * n + 127) / 128, 4096);
         if ((mode == TRI_PANEL || mode == TRI_BACK) && ncols <= 0) return;
-        const size_t smem = sizeof(double) * ((size_t)nb * (nb + 1) + (size_t)nb * 128);
         ctx->prof_pre(3100 + mode);
-        rt_launch(k_tri, grid, 128, smem, ctx->stream, t);
+        if (mode == TRI_SYM || mode == TRI_EYE) {
+            rt_launch(k_tri_fill, std::min<long long>(((long long)n * n + 127) / 128, 4096), 128, 0, ctx->stream, t);
+        } else if (mode == TRI_POTRF) {
+            rt_launch(k_potrf, 1, 256, sizeof(double) * ((size_t)kNb * (kNb + 1) + 2 * kNb), ctx->stream, t);
+        } else {
+            rt_launch(k_trsolve, (ncols + kTriCols - 1) / kTriCols, kTriCols,
+                      sizeof(double) * ((size_t)kNb * (kNb + 1) + (size_t)kNb * kTriCols + kNb), ctx->stream, t);
+        }
         ctx->prof_post();
         ctx->launches++;
     }

@@ -51,6 +51,7 @@
 // optimisation fence on a 32-bit value: stops the compiler from precomputing (and spilling) the
 // addresses of a later phase at the top of the kernel
 #define SIMT_OPAQUE_U32(x) asm volatile("" : "+r"(x))
+#define SIMT_RSQRT(x) rsqrt(x)
 #define SIMT_KERNEL(name, params_t, body_call)                                   \
     __global__ void name(const params_t P) {                                     \
         extern __shared__ __align__(16) unsigned char simt_smem[];               \
@@ -79,6 +80,7 @@
 #define SIMT_PREFETCH_L2(ptr) ((void)0)
 #define SIMT_PREFETCH_L1(ptr) ((void)0)
 #define SIMT_OPAQUE_U32(x) ((void)0)
+#define SIMT_RSQRT(x) (1.0 / sqrt(x))
 #define SIMT_MBAR_INIT(mbar, count) ((void)0)
 #define SIMT_BULK_G2S(dst, src, bytes, mbar) memcpy((dst), (src), (bytes))
 #define SIMT_MBAR_WAIT(mbar, parity) ((void)0)

@@ -145,11 +145,13 @@ def test_polyfit_reference_model(pkg, emu_ctx, layout):
     assert out["cg_step"] < 1e-8 and out["dense_step"] < 1e-9, out
 
 
-def test_dense_linear_model(pkg, emu_ctx):
-    """FullJacobianFunc + FullResidualSampler shape (dense J, MatrixInversion) at a size the
-    emulator handles; tile edges are exercised (96 x 40 does not fill a 128 x 128 x 16 tile)."""
+@pytest.mark.parametrize("m,k,n", [(96, 40, 3), (128, 100, 2)])
+def test_dense_linear_model(pkg, emu_ctx, m, k, n):
+    """FullJacobianFunc + FullResidualSampler shape (dense J, MatrixInversion) at sizes the
+    emulator handles; tile edges are exercised (96 x 40 does not fill a 128 x 128 x 16 tile; k = 100
+    is one full 64-column Cholesky block, its panel and trailing update, and a short last block)."""
     from helpers import check_dense_ops
-    cfg = pkg.synthetic.dense_linear_config(96, 40, 3)
+    cfg = pkg.synthetic.dense_linear_config(m, k, n)
     out = check_dense_ops(pkg, emu_ctx, cfg)
     for k in ("metric", "residuals", "dense", "L", "kl", "grad", "mean_metric", "dense_step_residuals"):
         assert out[k] < 1e-10, (k, out)
@@ -215,4 +217,36 @@ def test_mvnormal_pushfwd_function(pkg, emu_ctx):
     assert rel(f(z), L @ z + c) < 1e-9
     Z = np.random.default_rng(4).standard_normal((5, 3))
     assert rel(f(Z), L @ Z + c[:, None]) < 1e-9
+    m.close()
+
+
+@pytest.mark.parametrize("dims", [(1,), (2,), (3,), (1, 8), (8, 1), (1, 1, 8), (1, 5), (2, 2)])
+def test_degenerate_shapes(pkg, emu_ctx, dims):
+    """Singleton axes, one-pixel and two-pixel fields: metric product and CG residuals vs the oracle."""
+    from helpers import TIGHT_O
+    cfg = _field(pkg, dims, "LIKE_POISSON", 2)
+    m = pkg.model_from_config(cfg, emu_ctx)
+    om = oracle_model(cfg)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(**TIGHT), emu_ctx)
+    V = np.random.default_rng(1).standard_normal((m.n_theta, 2))
+    lin = om.linearize(cfg["center"])
+    MVo = np.stack([O.metric_apply(lin, V[:, i]) for i in range(2)], axis=1)
+    assert rel(s.metric_apply(V), MVo) < 1e-12
+    R = pkg.sample_residuals(s, 2, draws=(cfg["Z1"], cfg["Z2"]))
+    Ro, _, _ = O.sample_residuals_cg(om, cfg["center"], cfg["Z1"], cfg["Z2"], **TIGHT_O)
+    assert rel(R, Ro) < RTOL
+    m.close()
+
+
+def test_empty_batches(pkg, emu_ctx):
+    """Zero residual samples / zero probe vectors: n_theta x 0 results, as the reference's
+    `sample_residuals(s, 0)` gives; the averaged quantities refuse an empty sample set."""
+    cfg = _field(pkg, (16, 8), "LIKE_NORMAL", 2)
+    m = pkg.model_from_config(cfg, emu_ctx)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(), emu_ctx)
+    assert pkg.sample_residuals(s, 0).shape == (m.n_theta, 0)
+    assert s.metric_apply(np.zeros((m.n_theta, 0))).shape == (m.n_theta, 0)
+    assert pkg.build_samples(m, np.zeros((m.n_theta, 0)), cfg["center"]).shape == (m.n_theta, 0)
+    with pytest.raises(pkg.MGVIB200Error):
+        pkg.kl_value_grad(m, cfg["center"], np.zeros((m.n_theta, 0)))
     m.close()

@@ -237,3 +237,33 @@ def test_c2_1d_65536_poisson(pkg, gpu_ctx):
 def test_long_1d_other_lengths(pkg, gpu_ctx, N):
     cfg = _field(pkg, (N,), "LIKE_NORMAL", 3, layout=2)
     assert_field_ops(check_field_ops(pkg, gpu_ctx, cfg, check_step=(N <= 32768)), cfg)
+
+
+@pytest.mark.parametrize("dims", [(1,), (2,), (3,), (1, 8), (8, 1), (1, 1, 8), (1, 5), (2, 2)])
+def test_degenerate_shapes(pkg, gpu_ctx, dims):
+    """Singleton axes, one-pixel and two-pixel fields."""
+    from helpers import TIGHT_O
+    cfg = _field(pkg, dims, "LIKE_POISSON", 2)
+    m = pkg.model_from_config(cfg, gpu_ctx)
+    om = oracle_model(cfg)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(**TIGHT), gpu_ctx)
+    V = np.random.default_rng(1).standard_normal((m.n_theta, 2))
+    lin = om.linearize(cfg["center"])
+    MVo = np.stack([O.metric_apply(lin, V[:, i]) for i in range(2)], axis=1)
+    assert rel(s.metric_apply(V), MVo) < 1e-12
+    R = pkg.sample_residuals(s, 2, draws=(cfg["Z1"], cfg["Z2"]))
+    Ro, _, _ = O.sample_residuals_cg(om, cfg["center"], cfg["Z1"], cfg["Z2"], **TIGHT_O)
+    assert rel(R, Ro) < RTOL
+    m.close()
+
+
+def test_empty_batches(pkg, gpu_ctx):
+    """Zero residual samples / probe vectors give n_theta x 0 results without a launch."""
+    cfg = _field(pkg, (16, 8), "LIKE_NORMAL", 2)
+    m = pkg.model_from_config(cfg, gpu_ctx)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(), gpu_ctx)
+    assert pkg.sample_residuals(s, 0).shape == (m.n_theta, 0)
+    assert s.metric_apply(np.zeros((m.n_theta, 0))).shape == (m.n_theta, 0)
+    with pytest.raises(pkg.MGVIB200Error):
+        pkg.kl_value_grad(m, cfg["center"], np.zeros((m.n_theta, 0)))
+    m.close()
