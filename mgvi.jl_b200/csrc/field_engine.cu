@@ -49,7 +49,11 @@ struct FieldEngine : Engine {
     int prefetch_epi = 0;       // L1 hints for post-transform operands (MGVIB200_PREFETCH_EPI)
     int stage_vin = 0;          // TMA bulk staging of the '+ v' rows in the hot last pass (needs -DMGVI_STAGE_VIN; MGVIB200_STAGE_VIN=1)
 
-    DevBuf A, data, w, q, wbar, center;
+    DevBuf A, data, w, q, wbar, center, w_tiled, ws_tile;
+    const double* w_tiled_src = nullptr;   // which weight array w_tiled mirrors, and at which generation
+    long long w_gen = 0, w_tiled_gen = -1;
+    int w_tiled_lg_wt = 0;
+    int tiled_mode = -1;        // tile-major scratch for 2-D narrow column tiles: -1 auto, 0 off, 1 force (MGVIB200_TILED)
     std::map<long long, DevBuf> tw, cas;
     ReduceWs rws;
     CgWs cgws, ncgws;
@@ -64,7 +68,7 @@ struct FieldEngine : Engine {
     int h_ncg[2] = {0, 0};
 
     ~FieldEngine() override {
-        DevBuf* all[] = {&A, &data, &w, &q, &wbar, &center, &ws_r, &ws_p, &ws_t, &pt_t, &acc, &qsum, &n_x, &n_r,
+        DevBuf* all[] = {&A, &data, &w, &q, &wbar, &center, &w_tiled, &ws_tile, &ws_r, &ws_p, &ws_t, &pt_t, &acc, &qsum, &n_x, &n_r,
                          &n_p, &n_t, &tmpA, &tmpB, &rws.partials, &rws.counters, &rws.red};
         for (auto* b : all) b->release();
         for (auto& kv : tw) kv.second.release();
@@ -112,6 +116,7 @@ struct FieldEngine : Engine {
         if (const char* e = getenv("MGVIB200_NO_HOT")) use_hot = !atoi(e);
         if (const char* e = getenv("MGVIB200_PREFETCH_EPI")) prefetch_epi = atoi(e);
         if (const char* e = getenv("MGVIB200_STAGE_VIN")) stage_vin = atoi(e);
+        if (const char* e = getenv("MGVIB200_TILED")) tiled_mode = atoi(e);
         if (getenv("MGVIB200_FORCE_GENERIC") && atoi(getenv("MGVIB200_FORCE_GENERIC"))) big = false;
         if (!fast)
             for (int i = 0; i < ndim; ++i)
@@ -569,19 +574,48 @@ struct FieldEngine : Engine {
             launch_pass<GEO_PAIRVEC, PRO, EPI_METRIC, true>(P, geo_axis(0, nvec), nvec, 1, 1);
             return;
         }
+        // 2-D with narrow column tiles (rows of 2L reals < one 128-byte line): keep the scratch and the
+        // weight tile-major so the column pass reads and writes whole lines (field_pass.h)
+        int lg_wt = 0, lg_rows = 0;
+        if (ndim == 2 && tiled_mode != 0) {
+            const PassGeo g0 = geo_axis(0, nvec);
+            const long long wt = 2LL * g0.L;
+            if (g0.geo == GEO_STRIDED && (tiled_mode == 1 || wt < 16) && (dims[1] / 8) % wt == 0 && dims[1] >= 8 * wt) {
+                lg_wt = ilog2((int)wt); lg_rows = g0.log2n;
+                if (w_tiled_src != P.w || w_tiled_gen != w_gen || w_tiled_lg_wt != lg_wt) {
+                    w_tiled.ensure(sizeof(double) * N);
+                    VecParams T;
+                    memset(&T, 0, sizeof T);
+                    T.op = VOP_TILE; T.nvec = 1; T.N = N; T.in = P.w; T.out = w_tiled.as<double>();
+                    T.lg_wt = lg_wt; T.lg_rows = lg_rows; T.lg_cols = ilog2((int)dims[1]);
+                    vec_launch(ctx, rws, T);
+                    w_tiled_src = P.w; w_tiled_gen = w_gen; w_tiled_lg_wt = lg_wt;
+                }
+                // the CG chains write A p over their scratch (same rows in, same rows out); with the
+                // scratch tile-major the last pass would overwrite tiles other blocks still have to
+                // read, so the scratch becomes a buffer of its own
+                if (scratch == P.out) {
+                    ws_tile.ensure(sizeof(double) * N * nvec);
+                    scratch = ws_tile.as<double>();
+                }
+            }
+        }
         {
             FieldPassParams Q = P;
             Q.out = scratch; Q.out_ld = N; Q.fin = FIN_NONE;
+            Q.t_lg_wt = lg_wt; Q.t_lg_rows = lg_rows;
             launch_pass<GEO_CONTIG, PRO, EPI_STORE, false>(Q, geo_axis(ndim - 1, nvec), nvec, nvec, 1);
         }
         FieldPassParams S = P;
         S.in = scratch; S.in_ld = N; S.out = scratch; S.out_ld = N; S.fin = FIN_NONE;
+        if (lg_wt) { S.w = w_tiled.as<double>(); S.t_lg_wt = lg_wt; S.t_lg_rows = lg_rows; }
         for (int a = ndim - 2; a >= 1; --a) launch_pass<GEO_STRIDED, PRO_LOAD, EPI_STORE, false>(S, geo_axis(a, nvec), nvec, nvec, 1);
         launch_pass<GEO_STRIDED, PRO_LOAD, EPI_STORE, true>(S, geo_axis(0, nvec), nvec, nvec, 1);
         for (int a = 1; a <= ndim - 2; ++a) launch_pass<GEO_STRIDED, PRO_LOAD, EPI_STORE, false>(S, geo_axis(a, nvec), nvec, nvec, 1);
         {
             FieldPassParams Q = P;
             Q.in = scratch; Q.in_ld = N; Q.fin = fin; Q.red_out = red;
+            Q.t_lg_wt = lg_wt; Q.t_lg_rows = lg_rows;
             launch_pass<GEO_CONTIG, PRO_LOAD, EPI_METRIC, false>(Q, geo_axis(ndim - 1, nvec), nvec, nvec, 1);
         }
     }
@@ -609,6 +643,7 @@ struct FieldEngine : Engine {
         pt_t.ensure(sizeof(double) * N);
         chain_forward<PRO_POINT, EPI_LINEARIZE>(P, 1, pt_t.as<double>(), FIN_NONE, nullptr, FIN_NONE, nullptr, false);
         rt_d2d(center.p, x, sizeof(double) * N, ctx->stream);
+        ++w_gen;
     }
 
     void get_weights(double* w_host, double* q_host) override {
@@ -739,6 +774,7 @@ struct FieldEngine : Engine {
                                                                          nullptr, FIN_NONE, nullptr, true);
         vec_sum_chunks(ctx, rws, acc.as<double>(), N, (int)chunks, 1.0 / (double)n_glob, wbar.as<double>(), N);
         comm_allreduce_sum(ctx, wbar.as<double>(), N);
+        ++w_gen;
     }
 
     void mean_metric_apply(const double* u, double* out) override {

@@ -70,6 +70,7 @@ struct FieldPassParams {
     int mask_active;                          // skip vectors whose cg.active flag is 0 (CG iterations only)
     int prefetch_blocks;                      // > 0: hint the inputs of block (this + prefetch_blocks) into L2
     int prefetch_epi;                         // hint the epilogue / mid operands into L1 before the transform
+    int t_lg_wt, t_lg_rows;                   // tile-major scratch (2-D): log2(reals per tile row) (0 = natural), log2(rows)
     int stage_vin;                            // contiguous EPI_METRIC: TMA-stage the '+ v' rows into shared memory at block start
     // ---- reduction ------------------------------------------------------------------------
     int fin;
@@ -509,6 +510,12 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
             off_a = (unsigned)((2 * u) << log2n) + (unsigned)lt;
             off_b = off_a + (1u << log2n);
             step = (unsigned)n8;
+        } else if (P.t_lg_wt) {
+            // tile-major scratch (2-D, narrow tiles): tile u is one contiguous block [row][2L reals],
+            // so the 2L-real row segments of this pass are back to back instead of one per 128-byte line
+            off_a = (unsigned)((u << (lgL + 1 + log2n)) + ((long long)lt << (lgL + 1)) + 2 * l);
+            off_b = off_a + 1;
+            step = (unsigned)(n8 << (lgL + 1));
         } else {
             const long long o = u >> P.lg_tpo, cb = u & ((1LL << P.lg_tpo) - 1);
             off_a = (unsigned)(((o << log2n) + lt) * P.inner + (cb << (lgL + 1)) + 2 * l);
@@ -517,6 +524,17 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
         }
     } else {
         off_a = off_b = (unsigned)lt;
+    }
+    // row passes next to a tile-major column pass: the scratch operand (the output of the first
+    // pass, the input of the last) is addressed tile-major -- element (row r, column k) lives at
+    // (k / wt) * wt * rows + r * wt + k % wt; rows 2u and 2u+1 of a unit are wt reals apart
+    unsigned toff_a = off_a, toff_b = off_b, tstep = step;
+    if (GEO == GEO_CONTIG && P.t_lg_wt) {
+        const long long u = bt * P.G + g;
+        const int lw = P.t_lg_wt;
+        toff_a = (unsigned)((((long long)(lt >> lw)) << (lw + P.t_lg_rows)) + ((2 * u) << lw) + (lt & ((1 << lw) - 1)));
+        toff_b = toff_a + (1u << lw);
+        tstep = (unsigned)(((long long)(n8 >> lw)) << (lw + P.t_lg_rows));
     }
     int sa = 0, sb = 0;
     bool va = false, vb = false;
@@ -546,10 +564,24 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
             if (PRO == PRO_CG) {
                 pro_cg_block<GEO == GEO_STRIDED>(v, P.p, P.r, P.A, off_a, off_b, step, (long long)sa * P.N,
                                                  P.first_iter ? 0.0 : P.cg.beta[sa], P.first_iter != 0);
+            } else if (PRO == PRO_LOAD && GEO == GEO_CONTIG && P.t_lg_wt && n8 >= 32) {
+                // tile-major scratch, row pass: a unit's two rows sit wt reals apart, so lane pairs
+                // fetch 16 bytes of ONE row each (even lane: row a, columns k, k+1; odd lane: row b,
+                // columns k-1, k) and swap halves -- half the load instructions, whole 32-byte sectors
+                const int q = lt & 1;
+                const double* src = P.in + (long long)sa * P.in_ld;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const unsigned o = q ? (toff_b + m * tstep - 1) : (toff_a + m * tstep);
+                    const double2 d2 = *reinterpret_cast<const double2*>(src + o);
+                    const double rcv = SIMT_SHFL_XOR_F64(q ? d2.x : d2.y, 1);
+                    v[m] = q ? make_double2(rcv, d2.y) : make_double2(d2.x, rcv);
+                }
             } else {
 #pragma unroll
                 for (int m = 0; m < 8; ++m)
-                    v[m] = pro_pair<PRO>(P, sa, sb, off_a + m * step, off_b + m * step, true, true, adj, acc_a, acc_b);
+                    v[m] = (PRO == PRO_LOAD) ? pro_pair<PRO>(P, sa, sb, toff_a + m * tstep, toff_b + m * tstep, true, true, adj, acc_a, acc_b)
+                                             : pro_pair<PRO>(P, sa, sb, off_a + m * step, off_b + m * step, true, true, adj, acc_a, acc_b);
             }
         } else {
 #pragma unroll
@@ -633,10 +665,23 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
             } else if (EPI == EPI_METRIC) {
                 epi_metric_block<GEO == GEO_STRIDED>(v, P.out, P.vin, P.A, off_a, off_b, step, (long long)sa * P.out_ld,
                                                      (long long)sa * P.vin_ld, P.scale, acc_a);
+            } else if (EPI == EPI_STORE && GEO == GEO_CONTIG && P.t_lg_wt && n8 >= 32) {
+                // tile-major scratch, row pass: the mirror image of the paired load above
+                const int q = lt & 1;
+                double* dst = P.out + (long long)sa * P.out_ld;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const double rcv = SIMT_SHFL_XOR_F64(q ? v[m].x : v[m].y, 1);
+                    const unsigned o = q ? (toff_b + m * tstep - 1) : (toff_a + m * tstep);
+                    *reinterpret_cast<double2*>(dst + o) = q ? make_double2(rcv, v[m].y) : make_double2(v[m].x, rcv);
+                }
             } else {
 #pragma unroll
                 for (int m = 0; m < 8; ++m)
-                    epi_pair<EPI>(P, sa, sb, off_a + m * step, off_b + m * step, true, true, adj, v[m], acc_a, acc_b, accv[m]);
+                    if (EPI == EPI_STORE)
+                        epi_pair<EPI>(P, sa, sb, toff_a + m * tstep, toff_b + m * tstep, true, true, adj, v[m], acc_a, acc_b, accv[m]);
+                    else
+                        epi_pair<EPI>(P, sa, sb, off_a + m * step, off_b + m * step, true, true, adj, v[m], acc_a, acc_b, accv[m]);
             }
         }
     }

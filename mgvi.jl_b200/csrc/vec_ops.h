@@ -19,7 +19,8 @@ enum {
     VOP_CG_PAP = 8,      // acc = p . Ap                                       (per vector; dense CG)
     VOP_QUAD = 9,        // acc = sum x . (0.5 y - h)  over all vectors         (dense KL value)
     VOP_FLIP = 10,       // out[i, s] = in[N-1-i, s]                            (index reversal)
-    VOP_COPY = 11        // out = in                                            (per vector)
+    VOP_COPY = 11,       // out = in                                            (per vector)
+    VOP_TILE = 12        // out[tile-major i] = in[natural index of i]           (2-D relayout, field_pass.h)
 };
 
 struct VecParams {
@@ -29,6 +30,7 @@ struct VecParams {
     const double* in; double* out; long long in_ld;
     const double* y;
     int nsum;
+    int lg_wt, lg_rows, lg_cols;      // VOP_TILE geometry
     double a, scale;
     double* partials; unsigned* counters; double* red_out;
     CgScalars cg;
@@ -66,6 +68,11 @@ SIMT_DEVICE void vec_elem(const VecParams& P, int s, long long i, double alpha, 
         case VOP_QUAD: acc += P.in[gi] * (0.5 * P.y[gi] - P.Ap[i]); break;
         case VOP_FLIP: P.out[gi] = P.in[(long long)s * P.N + (P.N - 1 - i)]; break;
         case VOP_COPY: P.out[gi] = P.in[(long long)s * P.in_ld + i]; break;
+        case VOP_TILE: {
+            const long long tile = i >> (P.lg_wt + P.lg_rows), r = (i >> P.lg_wt) & ((1LL << P.lg_rows) - 1);
+            const long long k = (tile << P.lg_wt) + (i & ((1LL << P.lg_wt) - 1));
+            P.out[gi] = P.in[(long long)s * P.N + (r << P.lg_cols) + k];
+        } break;
         case VOP_BUILD: {
             const double c = P.in[i], rv = P.y[gi];
             P.out[(long long)(2 * s) * P.N + i] = c + rv;

@@ -250,3 +250,27 @@ def test_empty_batches(pkg, emu_ctx):
     with pytest.raises(pkg.MGVIB200Error):
         pkg.kl_value_grad(m, cfg["center"], np.zeros((m.n_theta, 0)))
     m.close()
+
+
+@pytest.mark.parametrize("dims,L", [((32, 64), 2), ((64, 128), 4), ((256, 32), 2), ((32, 256), 2)])
+def test_tile_major_scratch_forced(pkg, emu_ctx, monkeypatch, dims, L):
+    """Tile-major scratch/weight layout of the 2-D CG chain (what 2048-point columns use), forced on
+    at small sizes: every field operation incl. the full step against the oracle."""
+    monkeypatch.setenv("MGVIB200_TILED", "1")
+    monkeypatch.setenv("MGVIB200_STRIDED_L", str(L))
+    cfg = _field(pkg, dims, "LIKE_POISSON", 3)
+    assert_field_ops(check_field_ops(pkg, emu_ctx, cfg, check_step=(dims[0] < 256)), cfg)
+
+
+def test_tile_major_scratch_2048_columns(pkg, emu_ctx):
+    """The benchmark's column length with its default tile (2 complex columns -> tile-major scratch,
+    compile-time-shape kernels): metric product vs the oracle."""
+    cfg = _field(pkg, (2048, 32), "LIKE_NORMAL", 2, 0)
+    m = pkg.model_from_config(cfg, emu_ctx)
+    om = oracle_model(cfg)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(), emu_ctx)
+    V = np.random.default_rng(12).standard_normal((m.n_theta, 3))
+    lin = om.linearize(cfg["center"])
+    MVo = np.stack([O.metric_apply(lin, V[:, i]) for i in range(3)], axis=1)
+    assert rel(s.metric_apply(V), MVo) < 1e-12
+    m.close()
