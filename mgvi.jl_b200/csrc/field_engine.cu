@@ -53,6 +53,7 @@ struct FieldEngine : Engine {
     const double* w_tiled_src = nullptr;   // which weight array w_tiled mirrors, and at which generation
     long long w_gen = 0, w_tiled_gen = -1;
     int w_tiled_lg_wt = 0;
+    int row_threads = 256;      // target block size of the row (contiguous) passes (MGVIB200_ROW_THREADS)
     int tiled_mode = -1;        // tile-major scratch for 2-D narrow column tiles: -1 auto, 0 off, 1 force (MGVIB200_TILED)
     std::map<long long, DevBuf> tw, cas;
     ReduceWs rws;
@@ -117,6 +118,7 @@ struct FieldEngine : Engine {
         if (const char* e = getenv("MGVIB200_PREFETCH_EPI")) prefetch_epi = atoi(e);
         if (const char* e = getenv("MGVIB200_STAGE_VIN")) stage_vin = atoi(e);
         if (const char* e = getenv("MGVIB200_TILED")) tiled_mode = atoi(e);
+        if (const char* e = getenv("MGVIB200_ROW_THREADS")) row_threads = std::max(32, atoi(e));
         if (getenv("MGVIB200_FORCE_GENERIC") && atoi(getenv("MGVIB200_FORCE_GENERIC"))) big = false;
         if (!fast)
             for (int i = 0; i < ndim; ++i)
@@ -272,7 +274,7 @@ struct FieldEngine : Engine {
         } else if (axis == ndim - 1) {
             g.geo = GEO_CONTIG; g.L = 1;
             g.units_per_vec = (N / g.n) / 2;
-            long long G = std::max<long long>(1, 256 / tpl);
+            long long G = std::max<long long>(1, row_threads / tpl);
             G = std::min(G, g.units_per_vec);
             G = std::max<long long>(G, (32 + tpl - 1) / tpl);
             g.G = (int)G;
@@ -327,9 +329,10 @@ struct FieldEngine : Engine {
         }
 #endif
         constexpr int upt = (LG > 0) ? (1 << (LG - 3 + LGL)) : 256;
-        if (upt <= 256)
+        (void)upt;
+        if (g.threads <= 256)
             rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 256, MGVI_MINB, LG, LGL, false>, grid, g.threads, g.smem, ctx->stream, P);
-        else if (upt == 512)
+        else if (g.threads <= 512)
             rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 512, 2, LG, LGL, false>, grid, g.threads, g.smem, ctx->stream, P);
         else
             rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 1024, 1, LG, LGL, false>, grid, g.threads, g.smem, ctx->stream, P);
