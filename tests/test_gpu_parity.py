@@ -158,6 +158,15 @@ def test_full_size_c3_2048x2048(pkg, gpu_ctx):
     _full_metric_checks(pkg, gpu_ctx, cfg, 2)
 
 
+@pytest.mark.parametrize("dims,like", [((4096, 4096), "LIKE_POISSON"), ((2048, 512), "LIKE_NORMAL"),
+                                       ((512, 2048), "LIKE_POISSON"), ((1024, 4096), "LIKE_NORMAL")])
+def test_large_2d_shapes(pkg, gpu_ctx, dims, like):
+    """Largest supported axis lengths and non-square fields: 1024-thread column tiles, tile-major
+    scratch with 2- and 4-column tiles next to natural-layout 8-column tiles."""
+    cfg = _field(pkg, dims, like, 1)
+    _full_metric_checks(pkg, gpu_ctx, cfg, 1)
+
+
 def test_full_size_c5_256cubed(pkg, gpu_ctx):
     cfg = _field(pkg, (256, 256, 256), "LIKE_POISSON", 1)
     _full_metric_checks(pkg, gpu_ctx, cfg, 1)
