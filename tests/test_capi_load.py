@@ -79,3 +79,51 @@ def test_config_defaults_match_reference(pkg):
     o = cfg.optimizer                                   # src/newtoncg.jl:14-31
     assert (o.alpha, o.steps, o.i0, o.i1) == (0.1, 4, 5, 50)
     assert pkg.mgvi_kl_optimize_step is pkg.mgvi_step
+
+
+def _balanced(src, start):
+    """text of the parenthesised group opening at src[start] == '(' (without the outer parens)"""
+    depth = 0
+    for i in range(start, len(src)):
+        if src[i] == "(":
+            depth += 1
+        elif src[i] == ")":
+            depth -= 1
+            if depth == 0:
+                return src[start + 1:i]
+    raise ValueError("unbalanced")
+
+
+def _top_level_count(text):
+    text = text.strip()
+    if not text or text == "void":
+        return 0
+    depth, n = 0, 1
+    for ch in text:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        elif ch == "," and depth == 0:
+            n += 1
+    return n - (1 if text.endswith(",") else 0)
+
+
+def test_julia_shim_matches_the_header():
+    """julia/MGVIB200.jl cannot be executed here (no Julia): at least every `ccall` in it must
+    name a symbol the header declares, with as many argument types as the C prototype has
+    parameters."""
+    hdr = open(os.path.join(ROOT, "include", "mgvi_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", "", hdr)
+    proto = {}
+    for m in re.finditer(r"\b(mgvib200_[a-z0-9_]+)\s*\(", hdr):
+        proto[m.group(1)] = _top_level_count(_balanced(hdr, m.end() - 1))
+    jl = open(os.path.join(ROOT, "julia", "MGVIB200.jl")).read()
+    calls = list(re.finditer(r"ccall\(\(:(mgvib200_[a-z0-9_]+),\s*libmgvib200\),\s*[A-Za-z{}.]+,\s*\(", jl))
+    assert len(calls) >= 12
+    for m in calls:
+        name = m.group(1)
+        assert name in proto, "shim calls undeclared symbol %s" % name
+        ntypes = _top_level_count(_balanced(jl, m.end() - 1))
+        assert ntypes == proto[name], (name, ntypes, proto[name])
