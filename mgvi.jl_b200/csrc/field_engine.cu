@@ -371,13 +371,20 @@ struct FieldEngine : Engine {
                                ((PRO == PRO_CG && EPI == EPI_STORE) || (PRO == PRO_LOAD && EPI == EPI_METRIC));
         constexpr bool hot_s = (GEO == GEO_STRIDED) && (PRO == PRO_LOAD && EPI == EPI_STORE);
         bool done = false;
+        // `if constexpr`: only the shape classes that have a specialised build instantiate one
         if (nloop == 1 && use_hot) {
-            if (hot_c && g.log2n == 11) { launch_hot<GEO, PRO, EPI, DBL, hot_c ? 11 : 0, 0>(P, g, grid); done = true; }
-            else if (hot_c && g.log2n == 8) { launch_hot<GEO, PRO, EPI, DBL, hot_c ? 8 : 0, 0>(P, g, grid); done = true; }
-            else if (hot_s && DBL && g.log2n == 11 && g.lgL == 2) { launch_hot<GEO, PRO, EPI, DBL, (hot_s && DBL) ? 11 : 0, 2>(P, g, grid); done = true; }
-            else if (hot_s && DBL && g.log2n == 11 && g.lgL == 1) { launch_hot<GEO, PRO, EPI, DBL, (hot_s && DBL) ? 11 : 0, 1>(P, g, grid); done = true; }
-            else if (hot_s && g.log2n == 8 && g.lgL == 3) { launch_hot<GEO, PRO, EPI, DBL, hot_s ? 8 : 0, 3>(P, g, grid); done = true; }
-            else if (hot_s && g.log2n == 8 && g.lgL == 2) { launch_hot<GEO, PRO, EPI, DBL, hot_s ? 8 : 0, 2>(P, g, grid); done = true; }
+            if constexpr (hot_c) {
+                if (g.log2n == 11) { launch_hot<GEO, PRO, EPI, DBL, 11, 0>(P, g, grid); done = true; }
+                else if (g.log2n == 8) { launch_hot<GEO, PRO, EPI, DBL, 8, 0>(P, g, grid); done = true; }
+            }
+            if constexpr (hot_s && DBL) {
+                if (g.log2n == 11 && g.lgL == 2) { launch_hot<GEO, PRO, EPI, DBL, 11, 2>(P, g, grid); done = true; }
+                else if (g.log2n == 11 && g.lgL == 1) { launch_hot<GEO, PRO, EPI, DBL, 11, 1>(P, g, grid); done = true; }
+            }
+            if constexpr (hot_s) {
+                if (!done && g.log2n == 8 && g.lgL == 3) { launch_hot<GEO, PRO, EPI, DBL, 8, 3>(P, g, grid); done = true; }
+                else if (!done && g.log2n == 8 && g.lgL == 2) { launch_hot<GEO, PRO, EPI, DBL, 8, 2>(P, g, grid); done = true; }
+            }
         }
         if (!done) launch_lg<GEO, PRO, EPI, DBL>(P, g, grid);
         ctx->prof_post();
