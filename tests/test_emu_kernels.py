@@ -274,3 +274,34 @@ def test_tile_major_scratch_2048_columns(pkg, emu_ctx):
     MVo = np.stack([O.metric_apply(lin, V[:, i]) for i in range(3)], axis=1)
     assert rel(s.metric_apply(V), MVo) < 1e-12
     m.close()
+
+
+def _random_shapes(seed, count):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < count:
+        d = int(rng.integers(1, 4))
+        dims = tuple(int(rng.choice([1, 3, 5, 8, 8, 12, 16, 16, 32, 32, 64, 128])) for _ in range(d))
+        if 2 <= int(np.prod(dims)) <= 16384:
+            out.append(dims)
+    return out
+
+
+@pytest.mark.parametrize("dims", _random_shapes(2026, 24))
+def test_metric_random_shapes(pkg, emu_ctx, dims):
+    """Seeded random shapes mixing power-of-two (fast kernels) and other axis lengths (generic
+    path), 1-D to 3-D: metric product against the oracle, symmetry, and M >= I."""
+    like = "LIKE_POISSON" if sum(dims) % 2 else "LIKE_NORMAL"
+    cfg = _field(pkg, dims, like, 2)
+    m = pkg.model_from_config(cfg, emu_ctx)
+    om = oracle_model(cfg)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(), emu_ctx)
+    V = np.random.default_rng(3).standard_normal((m.n_theta, 2))
+    MV = s.metric_apply(V)
+    lin = om.linearize(cfg["center"])
+    MVo = np.stack([O.metric_apply(lin, V[:, i]) for i in range(2)], axis=1)
+    assert rel(MV, MVo) < 1e-12, dims
+    a, b = float(V[:, 0] @ MV[:, 1]), float(MV[:, 0] @ V[:, 1])
+    assert abs(a - b) <= 1e-11 * max(abs(a), abs(b), 1.0)
+    assert float(V[:, 0] @ MV[:, 0]) >= float(V[:, 0] @ V[:, 0]) * (1 - 1e-14)
+    m.close()
