@@ -283,3 +283,34 @@ def test_empty_batches(pkg, gpu_ctx):
     with pytest.raises(pkg.MGVIB200Error):
         pkg.kl_value_grad(m, cfg["center"], np.zeros((m.n_theta, 0)))
     m.close()
+
+
+def _random_shapes(seed, count):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < count:
+        d = int(rng.integers(1, 4))
+        dims = tuple(int(rng.choice([1, 3, 5, 8, 8, 12, 16, 16, 32, 32, 64, 128, 256, 512])) for _ in range(d))
+        if 2 <= int(np.prod(dims)) <= 65536:
+            out.append(dims)
+    return out
+
+
+@pytest.mark.parametrize("dims", _random_shapes(7, 16))
+def test_random_shapes(pkg, gpu_ctx, dims):
+    """Seeded random shapes (power-of-two and other axis lengths, 1-D to 3-D): metric product and
+    CG residual samples against the oracle."""
+    from helpers import TIGHT_O
+    like = "LIKE_POISSON" if sum(dims) % 2 else "LIKE_NORMAL"
+    cfg = _field(pkg, dims, like, 3)
+    m = pkg.model_from_config(cfg, gpu_ctx)
+    om = oracle_model(cfg)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(**TIGHT), gpu_ctx)
+    V = np.random.default_rng(3).standard_normal((m.n_theta, 2))
+    lin = om.linearize(cfg["center"])
+    MVo = np.stack([O.metric_apply(lin, V[:, i]) for i in range(2)], axis=1)
+    assert rel(s.metric_apply(V), MVo) < 1e-12, dims
+    R = pkg.sample_residuals(s, 3, draws=(cfg["Z1"], cfg["Z2"]))
+    Ro, _, _ = O.sample_residuals_cg(om, cfg["center"], cfg["Z1"], cfg["Z2"], **TIGHT_O)
+    assert rel(R, Ro) < RTOL, dims
+    m.close()
