@@ -314,3 +314,16 @@ def test_random_shapes(pkg, gpu_ctx, dims):
     Ro, _, _ = O.sample_residuals_cg(om, cfg["center"], cfg["Z1"], cfg["Z2"], **TIGHT_O)
     assert rel(R, Ro) < RTOL, dims
     m.close()
+
+
+@pytest.mark.parametrize("m,k,n", [(65, 64, 1), (130, 65, 2), (200, 127, 3), (257, 128, 2), (400, 129, 4), (333, 191, 2),
+                                   (512, 192, 1), (300, 193, 3)])
+def test_dense_block_edges(pkg, gpu_ctx, m, k, n):
+    """Dense path around the Cholesky block size (64) and the GEMM tile (128): k = 64, 65, 127,
+    128, 129, 191, 192, 193 columns; odd row counts."""
+    from helpers import check_dense_ops
+    cfg = pkg.synthetic.dense_linear_config(m, k, n)
+    out = check_dense_ops(pkg, gpu_ctx, cfg, with_step=False)
+    for key in ("metric", "residuals", "dense", "L", "kl", "grad", "mean_metric"):
+        assert out[key] < 1e-10, (key, out)
+    assert out["L_lower"] == 0.0
