@@ -68,13 +68,39 @@ typedef int rt_event;
 inline void rt_set_device(int) {}
 inline rt_stream rt_stream_create() { return 0; }
 inline void rt_stream_destroy(rt_stream) {}
+// Emulated device allocations carry a guard zone on both sides: NaN-filled (so an out-of-bounds
+// READ poisons the results the tests compare) and checked on free (an out-of-bounds WRITE aborts
+// the test run with a message).  This stands in for compute-sanitizer memcheck, which the GPU
+// pool does not offer.
+static const size_t kEmuGuard = 4096;
+struct EmuAllocHeader { size_t bytes; unsigned long long magic; };
 inline void* rt_malloc(size_t bytes) {
     size_t b = bytes ? bytes : 16;
-    void* p = aligned_alloc(256, (b + 255) / 256 * 256);
-    memset(p, 0xff, b);      // NaN-poison: uninitialised reads show up in the results
-    return p;
+    const size_t body = (b + 255) / 256 * 256;
+    unsigned char* raw = (unsigned char*)aligned_alloc(256, kEmuGuard + body + kEmuGuard);
+    memset(raw, 0xff, kEmuGuard + body + kEmuGuard);      // NaN-poison: uninitialised / stray reads show up in the results
+    EmuAllocHeader h{b, 0x6d67766962323030ULL};
+    memcpy(raw, &h, sizeof h);
+    return raw + kEmuGuard;
 }
-inline void rt_free(void* p) { free(p); }
+inline void rt_free(void* p) {
+    if (!p) return;
+    unsigned char* raw = (unsigned char*)p - kEmuGuard;
+    EmuAllocHeader h;
+    memcpy(&h, raw, sizeof h);
+    bool ok = (h.magic == 0x6d67766962323030ULL);
+    if (ok) {
+        for (size_t i = sizeof h; i < kEmuGuard && ok; ++i) ok = (raw[i] == 0xff);
+        const unsigned char* tail = (const unsigned char*)p + h.bytes;
+        const size_t body = (h.bytes + 255) / 256 * 256;
+        for (size_t i = 0; i < (body - h.bytes) + kEmuGuard && ok; ++i) ok = (tail[i] == 0xff);
+    }
+    if (!ok) {
+        fprintf(stderr, "simt emulator: out-of-bounds WRITE next to a device allocation of %zu bytes\n", h.bytes);
+        abort();
+    }
+    free(raw);
+}
 inline void* rt_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 16); }
 inline void rt_host_free(void* p) { free(p); }
 inline void rt_h2d(void* d, const void* h, size_t b, rt_stream) { memcpy(d, h, b); }
