@@ -301,6 +301,14 @@ class MvNormalDiag:
 
 
 @dataclass
+class MvNormalFull:
+    """`MvNormal(mu, Sigma)` with a full covariance (src/information.jl:20-58): the one family whose
+    Fisher block is dense; flat parameters [mu; columns of the upper triangle of Sigma]."""
+    mu: Any
+    cov: Any
+
+
+@dataclass
 class Product:
     dists: list
 
@@ -308,9 +316,48 @@ class Product:
 NamedTupleDist = dict
 
 
+def _fisher_mvnormal_full(cov) -> np.ndarray:
+    # src/information.jl:20-58 in closed form: mean block inv(Sigma); covariance block
+    # C[(a,b),(c,d)] = P_ac P_bd + P_ad P_bc, halved once for every diagonal parameter (a == b, c == d)
+    cov = np.asarray(cov, dtype=np.float64)
+    d = cov.shape[0]
+    P = np.linalg.inv(cov)
+    idx = [(i, j) for j in range(d) for i in range(j + 1)]
+    nc = len(idx)
+    out = np.zeros((d + nc, d + nc))
+    out[:d, :d] = P
+    for m, (a, b) in enumerate(idx):
+        for n, (c, e) in enumerate(idx):
+            v = P[a, c] * P[b, e] + P[a, e] * P[b, c]
+            if a == b:
+                v *= 0.5
+            if c == e:
+                v *= 0.5
+            out[d + m, d + n] = v
+    return out
+
+
 def fisher_information(dist) -> np.ndarray:
-    """`MGVI.fisher_information(distribution)`: the diagonal of the Fisher information in the
-    order of `flat_params` (src/information.jl:12-18,60-96; src/shapes.jl:40-54)."""
+    """`MGVI.fisher_information(distribution)` in the order of `flat_params`
+    (src/information.jl:12-96; src/shapes.jl:40-54): a 1-D array (the diagonal) for the diagonal
+    families and their products -- what the device path consumes --, a dense 2-D array as soon as a
+    full-covariance `MvNormalFull` block is involved (host-side only)."""
+    if isinstance(dist, MvNormalFull):
+        return _fisher_mvnormal_full(dist.cov)
+    if isinstance(dist, (Product, dict)):
+        ds = (list(np.asarray(dist.dists, dtype=object).ravel(order="F")) if isinstance(dist, Product)
+              else list(dist.values()))
+        parts = [fisher_information(d) for d in ds]
+        if all(p.ndim == 1 for p in parts):
+            return np.concatenate(parts)
+        mats = [np.diag(p) if p.ndim == 1 else p for p in parts]
+        n = sum(m.shape[0] for m in mats)
+        out = np.zeros((n, n))
+        o = 0
+        for m in mats:
+            out[o:o + m.shape[0], o:o + m.shape[0]] = m
+            o += m.shape[0]
+        return out
     if isinstance(dist, Normal):
         inv = 1.0 / dist.sigma
         return np.array([inv * inv, 2.0 * (inv * inv)])
@@ -322,10 +369,6 @@ def fisher_information(dist) -> np.ndarray:
     if isinstance(dist, MvNormalDiag):
         inv = 1.0 / np.asarray(dist.var, dtype=np.float64)
         return np.concatenate([inv, 2.0 * inv])
-    if isinstance(dist, Product):
-        return np.concatenate([fisher_information(d) for d in np.asarray(dist.dists, dtype=object).ravel(order="F")])
-    if isinstance(dist, dict):
-        return np.concatenate([fisher_information(d) for d in dist.values()])
     raise MGVIB200Error("fisher_information: unsupported distribution %r" % (dist,))
 
 

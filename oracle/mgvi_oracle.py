@@ -24,7 +24,8 @@ __all__ = [
     "SQRT_EPS", "LAYOUT_MU_ONLY", "LAYOUT_BLOCKED", "LAYOUT_INTERLEAVED",
     "LINK_IDENTITY", "LINK_EXP", "LIKE_NORMAL", "LIKE_POISSON",
     "dht", "dht_matrix",
-    "fisher_normal", "fisher_mvnormal_diag", "fisher_exponential", "fisher_poisson", "fisher_blockdiag",
+    "fisher_normal", "fisher_mvnormal_diag", "fisher_mvnormal_full", "fisher_exponential", "fisher_poisson",
+    "fisher_blockdiag", "fisher_blockdiag_dense",
     "FieldModel", "PolyModel", "DenseLinearModel",
     "metric_apply", "sampler_rhs", "krylov_cg", "sample_residuals_cg", "residual_pushfwd_operator",
     "sample_residuals_dense", "mv_normal_logdensity", "posterior_loglike", "mean_neg_log_pstr",
@@ -99,6 +100,46 @@ def fisher_exponential(theta) -> np.ndarray:
 def fisher_poisson(lam) -> np.ndarray:
     """src/information.jl:74-78."""
     return np.array([1.0 / float(lam)])
+
+
+def fisher_mvnormal_full(mu, cov) -> np.ndarray:
+    """src/information.jl:20-58: MvNormal with a full covariance.  Flat parameters are
+    [mu (d); Sigma[0:i+1, i] for i = 0..d-1] (src/shapes.jl:14-21: columns of the upper triangle),
+    an off-diagonal Sigma_ab counting once for both symmetric entries.  Returns the dense
+    (d + d(d+1)/2)-square block matrix blockdiag(P, C), P = inv(Sigma),
+    C[(a,b),(c,d)] = 1/2 tr(P D_ab P D_cd), D_ab = dSigma/dSigma_ab (E_ab + E_ba, or E_aa) --
+    the closed form of the reference's loops (P_ac P_bd + P_ad P_bc, halved once per diagonal
+    parameter involved)."""
+    cov = np.asarray(cov, dtype=np.float64)
+    d = cov.shape[0]
+    P = np.linalg.inv(cov)
+    idx = [(i, j) for j in range(d) for i in range(j + 1)]
+    nc = len(idx)
+    C = np.zeros((nc, nc))
+    for m, (a, b) in enumerate(idx):
+        Dm = np.zeros((d, d)); Dm[a, b] = 1.0; Dm[b, a] = 1.0
+        for n, (c, e) in enumerate(idx):
+            Dn = np.zeros((d, d)); Dn[c, e] = 1.0; Dn[e, c] = 1.0
+            C[m, n] = 0.5 * np.trace(P @ Dm @ P @ Dn)
+    out = np.zeros((d + nc, d + nc))
+    out[:d, :d] = P
+    out[d:, d:] = C
+    return out
+
+
+def fisher_blockdiag_dense(parts) -> np.ndarray:
+    """`_blockdiag` (src/custom_linear_maps.jl:84-94) when at least one part is a dense block:
+    diagonal parts (1-D arrays) and dense parts (2-D arrays) on the diagonal of one matrix."""
+    mats = [np.diag(np.asarray(p, dtype=np.float64)) if np.ndim(p) == 1 else np.asarray(p, dtype=np.float64)
+            for p in parts]
+    n = sum(m.shape[0] for m in mats)
+    out = np.zeros((n, n))
+    o = 0
+    for m in mats:
+        k = m.shape[0]
+        out[o:o + k, o:o + k] = m
+        o += k
+    return out
 
 
 def fisher_blockdiag(parts) -> np.ndarray:

@@ -198,3 +198,55 @@ def test_oracle_matches_golden(name):
     assert rel(step["center"], gold["step_center"]) < 1e-11
     assert rel(step["samples"], gold["step_samples"]) < 1e-11
     assert step["trace"].cg_updates == gold["tr_cg_updates"].tolist()
+
+
+def _mvnormal_score_outer_mc(mu, cov, n, rng):
+    """Monte-Carlo E[g g'] of the score of MvNormal(mu, cov) in the reference's flat parameters
+    (mean, then the columns of the upper triangle of cov; test/information/information_utils.jl:
+    fisher_information_mc + _cut_params)."""
+    d = len(mu)
+    P = np.linalg.inv(cov)
+    X = rng.multivariate_normal(mu, cov, size=n)
+    Rm = X - mu
+    PR = Rm @ P                                   # rows: P r
+    idx = [(i, j) for j in range(d) for i in range(j + 1)]
+    G = np.empty((n, d + len(idx)))
+    G[:, :d] = PR
+    for m, (a, b) in enumerate(idx):
+        # d logp / d Sigma_ab (symmetric parameter) = (2 - [a == b]) * 1/2 (P r r' P - P)_ab
+        G[:, d + m] = (1.0 if a == b else 2.0) * 0.5 * (PR[:, a] * PR[:, b] - P[a, b])
+    return G.T @ G / n
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_fisher_mvnormal_full(pkg, dim):
+    """test/information/test_information.jl:31-46: full-covariance MvNormal Fisher block against the
+    Monte-Carlo estimate (5e-2, as the reference) and against the host mirror's closed form (which
+    is written from the reference's pair formula, the oracle's from the trace formula)."""
+    rng = np.random.default_rng(42 + dim)
+    A = rng.random((dim, dim))
+    cov = 5.0 * np.eye(dim) + 0.5 * (A + A.T)
+    mu = rng.random(dim)
+    F = O.fisher_mvnormal_full(mu, cov)
+    assert F.shape == (dim + dim * (dim + 1) // 2,) * 2
+    np.testing.assert_allclose(F, F.T, atol=1e-15)
+    np.testing.assert_allclose(pkg.fisher_information(pkg.api.MvNormalFull(mu, cov)), F, rtol=1e-12, atol=1e-15)
+    mc = _mvnormal_score_outer_mc(mu, cov, 200000, rng)
+    assert np.linalg.norm(F - mc) / np.linalg.norm(mc) < 5e-2
+    if dim == 1:       # a 1-d MvNormal is Normal parametrised by its variance: 1/var, 1/(2 var^2)
+        np.testing.assert_allclose(np.diag(F), [1.0 / cov[0, 0], 0.5 / cov[0, 0] ** 2], rtol=1e-13)
+
+
+def test_fisher_named_tuple_with_dense_block(pkg):
+    """test/information/test_information.jl:66-74: NamedTupleDist(a = Normal, b = Product of Normals,
+    c = full MvNormal) is the block diagonal of the parts, in order."""
+    api = pkg.api
+    cov = np.array([[2.0, 0.1], [0.1, 4.5]])
+    nt = {"a": api.Normal(0.1, 0.2), "b": api.Product([api.Normal(0.1, 0.2), api.Normal(0.3, 0.1)]),
+          "c": api.MvNormalFull([0.2, 0.3], cov)}
+    res = pkg.fisher_information(nt)
+    truth = O.fisher_blockdiag_dense([O.fisher_normal(0.1, 0.2),
+                                      O.fisher_blockdiag([O.fisher_normal(0.1, 0.2), O.fisher_normal(0.3, 0.1)]),
+                                      O.fisher_mvnormal_full([0.2, 0.3], cov)])
+    assert res.shape == (11, 11)
+    assert np.linalg.norm(res - truth) < 1e-5
