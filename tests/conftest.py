@@ -24,7 +24,8 @@ def emu_ctx(pkg):
     """Context on the g++/fiber-emulator build of the same sources (TEST INFRASTRUCTURE; the
     product never loads this library)."""
     import __graft_entry__ as g
-    path = g.build_emu()
+    # MGVIB200_EMU_LIB: run the emulator tier against a variant build (tools/build_variants.py --emu)
+    path = os.environ.get("MGVIB200_EMU_LIB") or g.build_emu()
     lib = pkg.Library(path)
     ctx = pkg.MGVIContext(library=lib)
     yield ctx
