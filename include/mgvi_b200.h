@@ -124,6 +124,16 @@ const char* mgvib200_version(void);
  *      all-reduces KL value / gradient input / mean metric weight over NCCL ---- */
 int mgvib200_comm_unique_id(uint8_t out_id[128]);
 int mgvib200_comm_init(mgvib200_ctx* ctx, int rank, int world_size, const uint8_t id[128]);
+/* Host-supplied collective instead of NCCL (an MPI communicator held by the Julia host, gloo in the
+ * CPU tests).  The only collective the library needs is an all-gather of doubles:
+ * recv[r*count .. (r+1)*count) = rank r's send[0 .. count); pointers are memory of the context's
+ * device, send may alias recv + rank*count; return 0 on success.  The library synchronises its
+ * stream before the call and expects the result to be complete when the callback returns.
+ * Sums over residual samples are formed in a fixed order from the gathered parts, so results do
+ * not depend on the number of ranks (1, 2, 4 or 8). */
+typedef int (*mgvib200_allgather_fn)(void* user, const double* send, double* recv, int64_t count);
+int mgvib200_comm_init_external(mgvib200_ctx* ctx, int rank, int world_size, mgvib200_allgather_fn allgather,
+                                void* user);
 
 /* ---- model (the `forward_model` argument of mgvi_step, src/mgvi_impl.jl:129-132) ---- */
 int mgvib200_model_create(mgvib200_ctx* ctx, const mgvib200_model_desc* desc, mgvib200_model** out);
@@ -162,6 +172,45 @@ int mgvib200_mean_metric_apply(mgvib200_model* m, const double* x, const double*
 /* a12  MGVI._optimize(f, adsel, Sigma_bar_inv, x0, ::NewtonCG, opts)  src/newtoncg.jl:85-167 */
 int mgvib200_newtoncg(mgvib200_model* m, const double* x0, const double* R, int64_t n,
                       const mgvib200_newtoncg_opts* opts, double* x, double* f, mgvib200_newtoncg_trace* trace);
+
+/* (f3)  The seam MGVI._optimize dispatches on for every other optimizer (ext/MGVIOptimExt.jl:12-23:
+ *      OnceDifferentiable(f, x0) handed to Optim; ext/MGVIOptimizationBaseExt.jl:19-36): the KL objective
+ *      f(x) = _mean_neg_log_pstr(model, data, R, x) and its gradient with the residual samples R held on
+ *      the device between evaluations.  bind copies R (n_theta x n) once; eval moves only x and grad. */
+int mgvib200_objective_bind(mgvib200_model* m, const double* R /* n_theta x n */, int64_t n);
+int mgvib200_objective_eval(mgvib200_model* m, const double* x /* n_theta */, double* f, double* grad_or_null);
+
+/* Parity probe of ONE Newton step (the loop body at src/newtoncg.jl:112-146): the caller injects the
+ * state the reference holds at the top of step `step` -- x_n, f_prev = f(x_n) as carried, df_n -- and
+ * gets back every intermediate of that step: grad f(x_n) (:115), the mean metric weight behind
+ * Sigma_bar_inv(x_n) (:120, mgvi_impl.jl:137-138), every inner-CG iterate dx_k with its residual norm
+ * and (steps >= 2) f(x_n - dx_k) (:121-139), the line-search evaluations in call order (:142), the
+ * accepted step beta and x_{n+1} (:143).  force_k > 0 performs exactly that many CG updates
+ * (teacher forcing); k_own_exit reports where the step's own exit rule (:124, :134) fired first.
+ * Test instrumentation for rows a12/a14; the same code path as mgvib200_newtoncg. */
+#define MGVIB200_PROBE_LS_MAX 96
+typedef struct {
+    /* inputs */
+    int64_t step;            /* 1-based Newton step number */
+    double f_prev, df_n;
+    int64_t force_k;         /* 0 = the step's own exit rule */
+    int64_t max_rec;         /* capacity of dx_iters (columns), f_k, cg_resid */
+    /* vector outputs, host memory, each may be NULL */
+    double* grad;            /* n_theta */
+    double* wbar;            /* FIELD_DHT: N */
+    double* dx_iters;        /* n_theta x max_rec */
+    double* f_k;             /* max_rec (NaN at step 1) */
+    double* cg_resid;        /* max_rec */
+    double* x_new;           /* n_theta */
+    /* scalar outputs */
+    int64_t k_done, k_own_exit;
+    double dphi0, beta, f_new;
+    int64_t n_ls;
+    int32_t ls_kind[MGVIB200_PROBE_LS_MAX];   /* 0 = phi(a), 1 = phi'(a) */
+    double ls_a[MGVIB200_PROBE_LS_MAX], ls_val[MGVIB200_PROBE_LS_MAX];
+} mgvib200_probe_rec;
+int mgvib200_newton_probe(mgvib200_model* m, const double* x_n, const double* R, int64_t n,
+                          const mgvib200_newtoncg_opts* opts, mgvib200_probe_rec* probe);
 
 /* a13  _build_samples  src/mgvi_impl.jl:152-156 : columns [c + r1, c - r1, c + r2, c - r2, ...] */
 int mgvib200_build_samples(mgvib200_model* m, const double* center, const double* R, int64_t n,

@@ -70,6 +70,21 @@ class MGVIContext:
         self.check(self.lib.comm_init(self.handle, rank, world_size, buf))
         self.rank, self.world_size = rank, world_size
 
+    def init_comm_external(self, rank: int, world_size: int, allgather):
+        """Host-supplied collective (mgvib200_comm_init_external): `allgather(send_ptr, recv_ptr, count)`
+        gathers `count` doubles from every rank into recv (rank-major); pointers are integers
+        (memory of the context's device)."""
+        def _cb(_user, send, recv, count):
+            try:
+                allgather(send, recv, int(count))
+                return 0
+            except Exception:       # noqa: BLE001 -- must not propagate through the C frame
+                return 1
+        self._allgather_cb = capi.ALLGATHER_FN(_cb)      # keep the trampoline alive
+        self.check(self.lib.comm_init_external(self.handle, rank, world_size,
+                                               C.cast(self._allgather_cb, C.c_void_p), None))
+        self.rank, self.world_size = rank, world_size
+
     def unique_id(self) -> bytes:
         buf = (C.c_uint8 * 128)()
         rc = self.lib.comm_unique_id(buf)
@@ -135,6 +150,54 @@ B200NewtonCG = NewtonCG
 
 
 @dataclass
+class LBFGS:
+    """Stands where `Optim.LBFGS()` / `OptimizationLBFGSB.LBFGSB()` stand in `MGVIConfig.optimizer`
+    (ext/MGVIOptimExt.jl:12-23, ext/MGVIOptimizationBaseExt.jl:19-36; exercised by
+    test/test_mgvi_impl.jl:44-60): a host-side quasi-Newton driver (SciPy L-BFGS-B) over the DEVICE
+    objective -- every f / grad f evaluation is `mgvib200_objective_eval` with the residual samples
+    resident in HBM.  `MGVIConfig.optimizer_opts` is forwarded as the solver options
+    (`Optim.Options(; optimization_opts...)`): maxiter, ftol, gtol, maxcor, ..."""
+    method: str = "L-BFGS-B"
+
+    def minimize(self, fun_and_grad, x0, opts):
+        import scipy.optimize
+        res = scipy.optimize.minimize(fun_and_grad, x0, jac=True, method=self.method, options=dict(opts or {}))
+        return np.asarray(res.x, dtype=np.float64), float(res.fun), res
+
+
+LBFGSB = LBFGS
+
+
+class KLObjective:
+    """`OnceDifferentiable(f, x0)` of the reference's Optim extension: f = _mean_neg_log_pstr over the
+    bound residual samples (src/mgvi_impl.jl:19-28), gradient by the analytic adjoint; evaluated on
+    the device."""
+
+    def __init__(self, forward_model: "_Model", R):
+        m = forward_model
+        self.model, self.ctx = m, m.context
+        R = np.asfortranarray(as_f64(R).reshape(m.n_theta, -1, order="F"))
+        self.ctx.check(self.ctx.lib.objective_bind(m.handle, ptr(R), R.shape[1]))
+        self.f_calls = 0
+
+    def __call__(self, x):
+        m = self.model
+        x = as_f64(x, (m.n_theta,))
+        f = C.c_double()
+        g = np.empty(m.n_theta)
+        self.ctx.check(self.ctx.lib.objective_eval(m.handle, ptr(x), C.byref(f), ptr(g)))
+        self.f_calls += 1
+        return float(f.value), g
+
+    def value(self, x):
+        m = self.model
+        x = as_f64(x, (m.n_theta,))
+        f = C.c_double()
+        self.ctx.check(self.ctx.lib.objective_eval(m.handle, ptr(x), C.byref(f), None))
+        return float(f.value)
+
+
+@dataclass
 class MGVIConfig:
     """`MGVIConfig(linsolver, optimizer, optimizer_opts)` (src/mgvi_impl.jl:51-55)."""
     linsolver: Any = field(default_factory=B200CG)
@@ -161,6 +224,20 @@ class _Model:
         self.context = context
         self.handle = None
         self._keep = []
+        self.data = None
+        # which ResidualSampler's linearisation currently sits in the device handle (the handle holds ONE
+        # linearisation: w, q and the centre); None after mgvi_step / mgvi_sample re-linearised it
+        self._lin_owner = None
+
+    def _check_data(self, data):
+        """`data` is part of the reference signature (src/mgvi_impl.jl:129-132); the declarative model
+        owns its observations, so a different array here is an error, not silently ignored."""
+        if data is None:
+            return
+        d = np.asarray(data, dtype=np.float64).ravel()
+        if d.shape != self.data.shape or not np.array_equal(d, self.data):
+            raise MGVIB200Error("`data` differs from the observations the model was built with; create a new "
+                                "model for new data")
 
     def _create(self, desc: capi.ModelDesc):
         h = C.c_void_p()
@@ -210,6 +287,7 @@ class CorrelatedFieldModel(_Model):
         desc.data, desc.n_data = ptr(d), N
         self._create(desc)
         self.dims = dims
+        self.data = d.ravel().copy()
 
     @classmethod
     def from_config(cls, cfg: dict, context: MGVIContext):
@@ -241,6 +319,7 @@ class PolynomialModel(_Model):
         desc.coef_scale = ptr(cs)
         desc.noise_scale = float(noise_scale)
         self._create(desc)
+        self.data = d.ravel().copy()
 
     @classmethod
     def from_config(cls, cfg: dict, context: MGVIContext):
@@ -264,6 +343,7 @@ class DenseLinearModel(_Model):
         desc.data, desc.n_data = ptr(d), m
         desc.J, desc.m, desc.k = ptr(J), m, k
         self._create(desc)
+        self.data = d.ravel().copy()
 
     @classmethod
     def from_config(cls, cfg: dict, context: MGVIContext):
@@ -380,8 +460,19 @@ def _cg_opts(solver) -> capi.CGOpts:
 
 
 def _draws(context: MGVIContext, rows: int, n: int) -> np.ndarray:
-    # one contiguous column per residual, in the order the reference consumes the stream
+    # dense sampler: one (n_theta x n) matrix, column-major (src/residual_samplers.jl:114,121)
     return context.rng.standard_normal((n, rows)).T
+
+
+def _draw_pairs(context: MGVIContext, n_lambda: int, n_theta: int, n: int):
+    """CG sampler draws in the order the reference consumes the stream (src/residual_samplers.jl:75-76,
+    once per residual, :88): for residual i first n1_i (n_lambda) then eta_i (n_theta)."""
+    Z1 = np.empty((n_lambda, n), order="F")
+    Z2 = np.empty((n_theta, n), order="F")
+    for i in range(n):
+        Z1[:, i] = context.rng.standard_normal(n_lambda)
+        Z2[:, i] = context.rng.standard_normal(n_theta)
+    return Z1, Z2
 
 
 class ResidualSampler:
@@ -396,10 +487,22 @@ class ResidualSampler:
         self.center_point = as_f64(center_point, (f_model.n_theta,))
         self.linear_solver = linear_solver
         self.context = context
-        context.check(context.lib.linearize(f_model.handle, ptr(self.center_point)))
+        self._linearize()
+
+    def _linearize(self):
+        self.context.check(self.context.lib.linearize(self.f_model.handle, ptr(self.center_point)))
+        self.f_model._lin_owner = self
+
+    def _ensure(self):
+        """The reference's sampler OWNS its linearisation (src/residual_samplers.jl:45-63); here the
+        device handle holds one linearisation at a time, so a sampler re-linearises at its own centre
+        whenever another sampler, mgvi_step or mgvi_sample has used the model since."""
+        if self.f_model._lin_owner is not self:
+            self._linearize()
 
     def metric_apply(self, V):
         """(J' F J + I) V for the columns of V (src/residual_samplers.jl:72)."""
+        self._ensure()
         V = as_f64(V).reshape(self.f_model.n_theta, -1, order="F")
         V = np.asfortranarray(V)
         out = np.empty_like(V, order="F")
@@ -407,6 +510,7 @@ class ResidualSampler:
         return out
 
     def weights(self):
+        self._ensure()
         N = self.f_model.n_lambda if self.f_model.kind != MODEL_FIELD_DHT else self.f_model.n_theta
         w, q = np.empty(N), np.empty(N)
         self.context.check(self.context.lib.get_weights(self.f_model.handle, ptr(w), ptr(q)))
@@ -440,6 +544,7 @@ def sample_residuals(s: ResidualSampler, n: int | None = None, draws=None, retur
     single = n is None
     n = 1 if single else int(n)
     m, ctx = s.f_model, s.context
+    s._ensure()
     R = np.empty((m.n_theta, n), order="F")
     info = {}
     if isinstance(s.linear_solver, MatrixInversion):
@@ -448,8 +553,7 @@ def sample_residuals(s: ResidualSampler, n: int | None = None, draws=None, retur
         ctx.check(ctx.lib.sample_residuals_dense(m.handle, ptr(Z), n, ptr(R), None))
     else:
         if draws is None:
-            Z1 = _draws(ctx, m.n_lambda, n)
-            Z2 = _draws(ctx, m.n_theta, n)
+            Z1, Z2 = _draw_pairs(ctx, m.n_lambda, m.n_theta, n)
         else:
             Z1, Z2 = draws
         Z1 = np.asfortranarray(as_f64(Z1).reshape(m.n_lambda, n, order="F"))
@@ -479,8 +583,7 @@ def _step_draws(model, n, dense, context, draws):
         Z1 = np.asfortranarray(as_f64(Z).reshape(model.n_theta, n, order="F"))
         return Z1, None
     if draws is None:
-        Z1 = _draws(context, model.n_lambda, n)
-        Z2 = _draws(context, model.n_theta, n)
+        Z1, Z2 = _draw_pairs(context, model.n_lambda, model.n_theta, n)
     else:
         Z1, Z2 = draws
     Z1 = np.asfortranarray(as_f64(Z1).reshape(model.n_lambda, n, order="F"))
@@ -491,12 +594,17 @@ def _step_draws(model, n, dense, context, draws):
 def mgvi_step(forward_model, data, n_residuals: int, center_init, config: MGVIConfig, context: MGVIContext,
               draws=None):
     """`mgvi_step(forward_model, data, n_residuals, center_init, config, context)`
-    (src/mgvi_impl.jl:129-144) -> (MGVIResult, updated_center).  `data` is owned by the
-    declarative model and only checked for presence here."""
+    (src/mgvi_impl.jl:129-144) -> (MGVIResult, updated_center).  `data` must be the observations the
+    declarative model was built with (or None); `config.optimizer_opts` is accepted by NewtonCG in the
+    reference but never read there (src/newtoncg.jl:85-167), so anything but an empty set is rejected."""
     if not isinstance(forward_model, _Model):
         raise MGVIB200Error("forward_model must be a declarative mgvi_b200 model; there is no CPU fallback")
+    forward_model._check_data(data)
     if not isinstance(config.optimizer, NewtonCG):
-        raise MGVIB200Error("only MGVI.NewtonCG is provided on the device path")
+        return _mgvi_step_host_optimizer(forward_model, n_residuals, center_init, config, context, draws)
+    if config.optimizer_opts:
+        raise MGVIB200Error("NewtonCG takes no optimizer_opts (src/newtoncg.jl:85-88 ignores them); got %r"
+                            % (dict(config.optimizer_opts),))
     m, n = forward_model, int(n_residuals)
     dense = isinstance(config.linsolver, MatrixInversion)
     center = as_f64(center_init, (m.n_theta,))
@@ -511,8 +619,27 @@ def mgvi_step(forward_model, data, n_residuals: int, center_init, config: MGVICo
     context.check(context.lib.step(m.handle, ptr(center), ptr(Z1), ptr(Z2) if Z2 is not None else None, n,
                                    1 if dense else 0, C.byref(cg), C.byref(opts), ptr(samples), ptr(center_out),
                                    C.byref(mnlp), iters.ctypes.data_as(capi.c_int64_p), C.byref(trace)))
+    m._lin_owner = None          # the step linearised the handle at center_init
     info = dict(linsolver_output=dict(iters=iters), optimizer_output=trace.as_dict())
     return MGVIResult(samples, float(mnlp.value), info), center_out
+
+
+def _mgvi_step_host_optimizer(m, n_residuals, center_init, config, context, draws):
+    """mgvi_step with `MGVI._optimize` dispatched to a host-side optimizer (the ext/*.jl methods): the
+    sampler and every objective / gradient evaluation run on the device, the optimizer's own vector
+    algebra on the host, exactly the split the reference's Optim extension has."""
+    opt = config.optimizer
+    if not hasattr(opt, "minimize"):
+        raise MGVIB200Error("optimizer must be MGVI.NewtonCG or provide minimize(fun_and_grad, x0, opts) "
+                            "(e.g. LBFGS()); got %r" % (opt,))
+    sampler = ResidualSampler(m, center_init, config.linsolver, context)
+    R, info = sample_residuals(sampler, int(n_residuals), draws=draws, return_info=True)
+    obj = KLObjective(m, R)
+    x, f_x, optres = opt.minimize(obj, sampler.center_point.copy(), config.optimizer_opts)
+    f_x = obj.value(x)                       # f(x_res) itself (ext/MGVIOptimizationBaseExt.jl:33)
+    samples = build_samples(m, R, x)
+    out = dict(linsolver_output=info, optimizer_output=optres)
+    return MGVIResult(samples, f_x, out), x
 
 
 mgvi_kl_optimize_step = mgvi_step
@@ -523,6 +650,7 @@ def mgvi_sample(forward_model, data, n_residuals: int, center, config: MGVIConfi
     """`mgvi_sample` (src/mgvi_impl.jl:166-174): samples at the given centre, no optimisation."""
     if not isinstance(forward_model, _Model):
         raise MGVIB200Error("forward_model must be a declarative mgvi_b200 model; there is no CPU fallback")
+    forward_model._check_data(data)
     m, n = forward_model, int(n_residuals)
     dense = isinstance(config.linsolver, MatrixInversion)
     c = as_f64(center, (m.n_theta,))
@@ -533,6 +661,7 @@ def mgvi_sample(forward_model, data, n_residuals: int, center, config: MGVIConfi
     context.check(context.lib.sample(m.handle, ptr(c), ptr(Z1), ptr(Z2) if Z2 is not None else None, n,
                                      1 if dense else 0, C.byref(cg), ptr(samples),
                                      iters.ctypes.data_as(capi.c_int64_p)))
+    m._lin_owner = None
     return samples
 
 
@@ -542,6 +671,7 @@ def mgvi_mvnormal_pushfwd_function(forward_model, data, config: MGVIConfig, cent
     (`MulAdd(residual_pushfwd_operator(sampler), center)`).  As in the reference this instantiates
     the metric densely (MatrixInversion), so it is for low-dimensional models; the product
     `L_Sigma z` runs on the device."""
+    forward_model._check_data(data)
     sampler = ResidualSampler(forward_model, center_point, MatrixInversion(), context)
     center = sampler.center_point.copy()
 
@@ -549,8 +679,7 @@ def mgvi_mvnormal_pushfwd_function(forward_model, data, config: MGVIConfig, cent
         z = as_f64(z)
         single = z.ndim == 1
         Z = np.asfortranarray(z.reshape(forward_model.n_theta, -1, order="F"))
-        # the sampler was linearised at `center`; re-linearise if the model has been used elsewhere since
-        context.check(context.lib.linearize(forward_model.handle, ptr(center)))
+        sampler._ensure()        # re-linearises at `center` if the model has been used elsewhere since
         R = np.empty_like(Z, order="F")
         context.check(context.lib.sample_residuals_dense(forward_model.handle, ptr(Z), Z.shape[1], ptr(R), None))
         out = center[:, None] + R
@@ -594,6 +723,34 @@ def newtoncg_optimize(forward_model: _Model, R, x0, optimizer: NewtonCG = Newton
     ctx.check(ctx.lib.newtoncg(m.handle, ptr(x0), ptr(R), R.shape[1], C.byref(opts), ptr(x), C.byref(f),
                                C.byref(trace)))
     return x, float(f.value), trace.as_dict()
+
+
+def newton_probe(forward_model: _Model, R, x_n, step: int, f_prev: float, df_n: float, *, force_k: int = 0,
+                 max_rec: int = 64, optimizer: NewtonCG = NewtonCG(), want_wbar: bool = True):
+    """One Newton step of `MGVI._optimize(::NewtonCG)` (src/newtoncg.jl:112-146) from an injected state,
+    with every intermediate returned (mgvib200_newton_probe): parity instrumentation for the
+    teacher-forced tests -- the same device code path as `newtoncg_optimize`."""
+    m, ctx = forward_model, forward_model.context
+    x_n = as_f64(x_n, (m.n_theta,))
+    R = np.asfortranarray(as_f64(R).reshape(m.n_theta, -1, order="F"))
+    pr = capi.NewtonProbe()
+    pr.step, pr.f_prev, pr.df_n, pr.force_k, pr.max_rec = int(step), float(f_prev), float(df_n), int(force_k), int(max_rec)
+    grad = np.empty(m.n_theta)
+    wbar = np.empty(m.n_theta) if (want_wbar and m.kind == MODEL_FIELD_DHT) else None
+    dx = np.full((m.n_theta, max_rec), np.nan, order="F")
+    f_k = np.full(max_rec, np.nan)
+    resid = np.full(max_rec, np.nan)
+    x_new = np.empty(m.n_theta)
+    pr.grad, pr.dx_iters, pr.f_k, pr.cg_resid, pr.x_new = ptr(grad), ptr(dx), ptr(f_k), ptr(resid), ptr(x_new)
+    pr.wbar = ptr(wbar) if wbar is not None else None
+    opts = _ncg_opts(optimizer)
+    ctx.check(ctx.lib.newton_probe(m.handle, ptr(x_n), ptr(R), R.shape[1], C.byref(opts), C.byref(pr)))
+    k = int(pr.k_done)
+    nls = int(pr.n_ls)
+    return dict(grad=grad, wbar=wbar, dx_iters=dx[:, :min(k, max_rec)], f_k=f_k[:min(k, max_rec)],
+                cg_resid=resid[:min(k, max_rec)], x_new=x_new, k_done=k, k_own_exit=int(pr.k_own_exit),
+                dphi0=float(pr.dphi0), beta=float(pr.beta), f_new=float(pr.f_new),
+                ls=[(int(pr.ls_kind[i]), float(pr.ls_a[i]), float(pr.ls_val[i])) for i in range(nls)])
 
 
 def build_samples(forward_model: _Model, R, center):

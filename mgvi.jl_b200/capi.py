@@ -52,6 +52,26 @@ class NewtonCGTrace(C.Structure):
                     minimum=float(self.minimum))
 
 
+# int (*mgvib200_allgather_fn)(void* user, const double* send, double* recv, int64_t count)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
+
+
+PROBE_LS_MAX = 96
+
+
+class NewtonProbe(C.Structure):
+    """mgvib200_newton_probe (include/mgvi_b200.h)."""
+    _fields_ = [
+        ("step", C.c_int64), ("f_prev", C.c_double), ("df_n", C.c_double), ("force_k", C.c_int64),
+        ("max_rec", C.c_int64),
+        ("grad", c_double_p), ("wbar", c_double_p), ("dx_iters", c_double_p), ("f_k", c_double_p),
+        ("cg_resid", c_double_p), ("x_new", c_double_p),
+        ("k_done", C.c_int64), ("k_own_exit", C.c_int64), ("dphi0", C.c_double), ("beta", C.c_double),
+        ("f_new", C.c_double), ("n_ls", C.c_int64), ("ls_kind", C.c_int32 * PROBE_LS_MAX),
+        ("ls_a", C.c_double * PROBE_LS_MAX), ("ls_val", C.c_double * PROBE_LS_MAX),
+    ]
+
+
 class CGOpts(C.Structure):
     _fields_ = [("abstol", C.c_double), ("reltol", C.c_double), ("maxiters", C.c_int64)]
 
@@ -64,6 +84,7 @@ EXPORTS = {
     "mgvib200_version": (C.c_char_p, []),
     "mgvib200_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "mgvib200_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint8)]),
+    "mgvib200_comm_init_external": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "mgvib200_model_create": (C.c_int, [C.c_void_p, C.POINTER(ModelDesc), C.POINTER(C.c_void_p)]),
     "mgvib200_model_destroy": (None, [C.c_void_p]),
     "mgvib200_model_n_theta": (C.c_int64, [C.c_void_p]),
@@ -78,6 +99,10 @@ EXPORTS = {
     "mgvib200_mean_metric_apply": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, c_double_p, c_double_p]),
     "mgvib200_newtoncg": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, C.POINTER(NewtonCGOpts),
                                     c_double_p, c_double_p, C.POINTER(NewtonCGTrace)]),
+    "mgvib200_objective_bind": (C.c_int, [C.c_void_p, c_double_p, C.c_int64]),
+    "mgvib200_objective_eval": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
+    "mgvib200_newton_probe": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, C.POINTER(NewtonCGOpts),
+                                        C.POINTER(NewtonProbe)]),
     "mgvib200_build_samples": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, c_double_p]),
     "mgvib200_step": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int,
                                 C.POINTER(CGOpts), C.POINTER(NewtonCGOpts), c_double_p, c_double_p, c_double_p,

@@ -24,7 +24,7 @@ struct BigParams {
     int lg_n1, lg_n2;           // n = n1 * n2
     int lgL, G;                 // lines side by side per unit, units per block
     long long units_per_pair;   // A: n2 / L tiles ; B*: n1 / 2 row pairs ; A': n2 / 2 column pairs
-    int npairs, nloop;          // pairs of vectors; loop over pairs inside a block (accumulating epilogues)
+    int npairs, nloop;          // pairs of vectors; nloop = 1 (one pair per block group)
     double2* cs;                // complex scratch [npairs][n]
     const double2* tw1;         // per-stage twiddles for length n1 (fft_core.h layout)
     const double2* tw2;         // ... for length n2
@@ -90,9 +90,6 @@ SIMT_DEVICE void big1d_body(const BigParams& B, unsigned char* smem_raw) {
     }
 
     double acc_a = 0.0, acc_b = 0.0;
-    double2 accv[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) accv[m] = make_double2(0.0, 0.0);
     int sa = 0, sb = 0;
     bool va = false, vb = false;
     for (int it = 0; it < B.nloop; ++it) {
@@ -181,28 +178,13 @@ SIMT_DEVICE void big1d_body(const BigParams& B, unsigned char* smem_raw) {
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
                 const long long pix = base + (long long)(lt + m * n8) * stride;
-                epi_pair<EPI>(P, sa, sb, pix, pix, va, vb, false, v[m], acc_a, acc_b, accv[m]);
+                epi_pair<EPI>(P, sa, sb, pix, pix, va, vb, false, v[m], acc_a, acc_b);
             }
         }
     }
-    if (KIND == BIG_A || KIND == BIG_B_START || KIND == BIG_B_MID) {
-        if (P.fin == FIN_TOTAL) {      // prologue reductions (prior term of the KL estimate)
-            const double tot = seg_reduce(acc_a + acc_b, SIMT_NTID, red);
-            block_publish_and_finalize(P.fin, P.cg, P.red_out, P.partials, P.counters, 0, SIMT_BID, SIMT_NBID, tot,
-                                       red, flag);
-        }
-        return;
-    }
-    // accumulated per-element outputs: one chunk per pair group, both halves of the pair summed
-    if ((EPI == EPI_KL && P.want_grad) || (EPI == EPI_LINEARIZE && P.acc_out != nullptr)) {
-        if (unit_ok) {
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const long long pix = base + (long long)(lt + m * n8) * stride;
-                P.acc_out[pgrp * n + pix] = accv[m].x + accv[m].y;
-            }
-        }
-    }
+    // reductions: prologue sums (prior term of the KL estimate) in the first kernel of a chain, epilogue
+    // sums (likelihood terms, CG dots) in the last; the middle kernels carry none
+    if ((KIND == BIG_B_START || KIND == BIG_B_MID) && P.fin != FIN_TOTAL) return;
     if (P.fin == FIN_NONE) return;
     if (P.fin == FIN_TOTAL) {
         const double tot = seg_reduce(acc_a + acc_b, SIMT_NTID, red);

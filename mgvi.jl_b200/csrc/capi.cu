@@ -9,6 +9,7 @@
 namespace mgvi {
 void comm_unique_id(uint8_t out[128]);
 void comm_init(mgvib200_ctx* ctx, int rank, int world, const uint8_t id[128]);
+void comm_init_external(mgvib200_ctx* ctx, int rank, int world, mgvib200_allgather_fn fn, void* user);
 void comm_destroy(mgvib200_ctx* ctx);
 }  // namespace mgvi
 
@@ -121,6 +122,113 @@ void strong_wolfe(const Fn1& phi, const Fn1& dphi, double alpha0, double phi0, d
 // MGVI._optimize(f, adsel, Sigma_bar_inv, x0, ::NewtonCG, opts) -- src/newtoncg.jl:85-167
 // All pointers device.  x_out may alias nothing else.
 // ----------------------------------------------------------------------------------------------
+struct NewtonScratch {
+    double *g, *trial, *gt;
+};
+
+NewtonScratch newton_scratch(mgvib200_ctx* ctx, long long N) {
+    const size_t b = sizeof(double) * N;
+    ctx->nw_g.ensure(b); ctx->nw_trial.ensure(b); ctx->nw_gt.ensure(b);
+    return NewtonScratch{ctx->nw_g.as<double>(), ctx->nw_trial.as<double>(), ctx->nw_gt.as<double>()};
+}
+
+void d2h_now(mgvib200_ctx* ctx, double* host, const double* dev, long long count) {
+    rt_d2h(host, dev, sizeof(double) * count, ctx->stream);
+    rt_sync(ctx->stream);
+}
+
+// One Newton step (the body of the loop at src/newtoncg.jl:112-146): x is updated in place, f_prev / df_n
+// are the carried scalars.  `rec` (parity probe, mgvib200_newton_probe) records every intermediate and may
+// force the number of inner CG updates; the product path passes null.
+void newton_one_step(mgvib200_model* m, double* x, const double* R, int64_t n, const mgvib200_newtoncg_opts& o,
+                     int64_t step, double& f_prev, double& df_n, double& f_n, mgvib200_newtoncg_trace& tr,
+                     mgvib200_probe_rec* rec) {
+    Engine* E = m->eng;
+    mgvib200_ctx* ctx = m->ctx;
+    const long long N = E->n_theta;
+    const size_t b = sizeof(double) * N;
+    NewtonScratch S = newton_scratch(ctx, N);
+    double* g = S.g; double* trial = S.trial; double* gt = S.gt;
+    ReduceWs& drws = ctx->drv_rws;
+    auto f = [&](const double* xp) { tr.f_calls++; return E->kl_value_grad(xp, R, n, nullptr); };
+    auto gradf = [&](const double* xp, double* gout) { tr.g_calls++; E->kl_value_grad(xp, R, n, gout); };
+    const int64_t force_k = rec ? rec->force_k : 0;
+    auto rec_iter = [&](int64_t k, double f_k) {
+        if (!rec || k > rec->max_rec) return;
+        if (rec->dx_iters) d2h_now(ctx, rec->dx_iters + (size_t)(k - 1) * N, E->ncg_dx(), N);
+        if (rec->f_k) rec->f_k[k - 1] = f_k;
+        if (rec->cg_resid) rec->cg_resid[k - 1] = E->ncg_residual();
+    };
+
+    gradf(x, g);                                           // :115
+    if (rec && rec->grad) d2h_now(ctx, rec->grad, g, N);
+    E->mean_metric_prepare(x, R, n);                       // Sigma_bar_inv(x_n), :120 / mgvi_impl.jl:137-138
+    if (rec && rec->wbar) E->get_mean_weights(rec->wbar);
+    E->ncg_init(g);
+    int64_t k = 0, own_exit = 0;
+    if (step == 1) {                                       // :121-127
+        while (E->ncg_active()) {
+            E->ncg_update(); ++k;
+            rec_iter(k, NAN);
+            if (k >= o.i0 && !own_exit) own_exit = k;
+            if (force_k > 0 ? k >= force_k : own_exit != 0) break;
+        }
+    } else {                                               // :129-139
+        double f_km1 = f_prev;
+        while (E->ncg_active()) {
+            E->ncg_update(); ++k;
+            vec_axpy(ctx, drws, trial, x, -1.0, E->ncg_dx(), N);
+            const double f_k = f(trial);
+            rec_iter(k, f_k);
+            if ((k >= o.i1 || fabs(f_k - f_km1) < o.alpha * df_n) && !own_exit) own_exit = k;
+            if (force_k > 0 ? k >= force_k : own_exit != 0) {
+                tr.cg_iterations[tr.n_cg_iterations++] = k;
+                break;
+            }
+            f_km1 = f_k;
+        }
+    }
+    tr.cg_updates[step - 1] = k;
+    const double* dx = E->ncg_dx();
+    if (k == 0) {
+        // the iterator yielded nothing: dx = 0 (cg_iterator! zeroes it)
+        ctx->nw_zero.ensure(b);
+        rt_memset(ctx->nw_zero.p, 0, b, ctx->stream);
+        dx = ctx->nw_zero.as<double>();
+    }
+    // line search along d = -dx (linesearch_args, :64-71): phi(a) = f(x + a d), phi'(a) = grad f(x + a d) . d
+    const double dphi0 = -vec_dot(ctx, drws, g, dx, N);
+    auto rec_ls = [&](int kind, double a, double v) {
+        if (!rec || rec->n_ls >= MGVIB200_PROBE_LS_MAX) return;
+        rec->ls_kind[rec->n_ls] = kind; rec->ls_a[rec->n_ls] = a; rec->ls_val[rec->n_ls] = v;
+        rec->n_ls++;
+    };
+    Fn1 phi = [&](double a) {
+        vec_axpy(ctx, drws, trial, x, -a, dx, N);
+        const double v = f(trial);
+        rec_ls(0, a, v);
+        return v;
+    };
+    Fn1 dphi = [&](double a) {
+        vec_axpy(ctx, drws, trial, x, -a, dx, N);
+        gradf(trial, gt);
+        const double v = -vec_dot(ctx, drws, gt, dx, N);
+        rec_ls(1, a, v);
+        return v;
+    };
+    double beta = 0.0;
+    strong_wolfe(phi, dphi, 1.0, f_prev, dphi0, beta, f_n);          // :142
+    tr.step_lengths[step - 1] = beta;
+    vec_axpy_inplace(ctx, drws, x, -beta, dx, N);                  // :143
+    df_n = fabs(f_n - f_prev);                                       // :144
+    f_prev = f_n;
+    tr.f_history[step] = f_n;                                        // :146
+    if (rec) {
+        rec->k_done = k; rec->k_own_exit = own_exit; rec->dphi0 = dphi0; rec->beta = beta; rec->f_new = f_n;
+        if (rec->x_new) d2h_now(ctx, rec->x_new, x, N);
+    }
+}
+
 void newtoncg_dev(mgvib200_model* m, const double* x0, const double* R, int64_t n,
                   const mgvib200_newtoncg_opts& o, double* x_out, double* f_out, mgvib200_newtoncg_trace* tr_out) {
     Engine* E = m->eng;
@@ -128,75 +236,21 @@ void newtoncg_dev(mgvib200_model* m, const double* x0, const double* R, int64_t 
     const long long N = E->n_theta;
     need(o.steps >= 0 && o.steps <= MGVIB200_TRACE_MAX, "NewtonCG: steps must be in [0, 64]");
     const size_t b = sizeof(double) * N;
-    ctx->nw_x.ensure(b); ctx->nw_g.ensure(b); ctx->nw_trial.ensure(b); ctx->nw_gt.ensure(b);
+    ctx->nw_x.ensure(b);
     double* x = ctx->nw_x.as<double>();
-    double* g = ctx->nw_g.as<double>();
-    double* trial = ctx->nw_trial.as<double>();
-    double* gt = ctx->nw_gt.as<double>();
-    ReduceWs& drws = ctx->drv_rws;
     mgvib200_newtoncg_trace tr;
     memset(&tr, 0, sizeof tr);
     rt_event_record(ctx->ev0, ctx->stream);
 
-    auto f = [&](const double* xp) { tr.f_calls++; return E->kl_value_grad(xp, R, n, nullptr); };
-    auto gradf = [&](const double* xp, double* gout) { tr.g_calls++; E->kl_value_grad(xp, R, n, gout); };
-
     rt_d2d(x, x0, b, ctx->stream);
-    double f_prev = f(x);                                  // :106
+    tr.f_calls++;
+    double f_prev = E->kl_value_grad(x, R, n, nullptr);   // :106
     tr.initial_f = f_prev;
     tr.f_history[0] = f_prev;
     tr.cg_iterations[tr.n_cg_iterations++] = o.i0;         // :108
     double f_n = 0.0, df_n = 0.0;
-    for (int64_t step = 1; step <= o.steps; ++step) {      // :112
-        gradf(x, g);                                       // :115
-        E->mean_metric_prepare(x, R, n);                   // Sigma_bar_inv(x_n), :120 / mgvi_impl.jl:137-138
-        E->ncg_init(g);
-        int64_t k = 0;
-        if (step == 1) {                                   // :121-127
-            while (E->ncg_active()) {
-                E->ncg_update(); ++k;
-                if (k >= o.i0) break;
-            }
-        } else {                                           // :129-139
-            double f_km1 = f_prev;
-            while (E->ncg_active()) {
-                E->ncg_update(); ++k;
-                vec_axpy(ctx, drws, trial, x, -1.0, E->ncg_dx(), N);
-                const double f_k = f(trial);
-                if (k >= o.i1 || fabs(f_k - f_km1) < o.alpha * df_n) {
-                    tr.cg_iterations[tr.n_cg_iterations++] = k;
-                    break;
-                }
-                f_km1 = f_k;
-            }
-        }
-        tr.cg_updates[step - 1] = k;
-        const double* dx = E->ncg_dx();
-        if (k == 0) {
-            // the iterator yielded nothing: dx = 0 (cg_iterator! zeroes it)
-            ctx->nw_zero.ensure(b);
-            rt_memset(ctx->nw_zero.p, 0, b, ctx->stream);
-            dx = ctx->nw_zero.as<double>();
-        }
-        // line search along d = -dx (linesearch_args, :64-71): phi(a) = f(x + a d), phi'(a) = grad f(x + a d) . d
-        const double dphi0 = -vec_dot(ctx, drws, g, dx, N);
-        Fn1 phi = [&](double a) {
-            vec_axpy(ctx, drws, trial, x, -a, dx, N);
-            return f(trial);
-        };
-        Fn1 dphi = [&](double a) {
-            vec_axpy(ctx, drws, trial, x, -a, dx, N);
-            gradf(trial, gt);
-            return -vec_dot(ctx, drws, gt, dx, N);
-        };
-        double beta = 0.0;
-        strong_wolfe(phi, dphi, 1.0, f_prev, dphi0, beta, f_n);      // :142
-        tr.step_lengths[step - 1] = beta;
-        vec_axpy_inplace(ctx, drws, x, -beta, dx, N);              // :143
-        df_n = fabs(f_n - f_prev);                                   // :144
-        f_prev = f_n;
-        tr.f_history[step] = f_n;                                    // :146
-    }
+    for (int64_t step = 1; step <= o.steps; ++step)        // :112
+        newton_one_step(m, x, R, n, o, step, f_prev, df_n, f_n, tr, nullptr);
     if (o.steps == 0) f_n = f_prev;
     tr.steps = o.steps;
     tr.minimum = f_n;
@@ -294,6 +348,12 @@ int mgvib200_comm_init(mgvib200_ctx* ctx, int rank, int world_size, const uint8_
     return guarded(ctx, [&] { rt_set_device(ctx->device); comm_init(ctx, rank, world_size, id); });
 }
 
+int mgvib200_comm_init_external(mgvib200_ctx* ctx, int rank, int world_size, mgvib200_allgather_fn allgather,
+                                void* user) {
+    if (!ctx) return MGVIB200_ERR_INVALID;
+    return guarded(ctx, [&] { rt_set_device(ctx->device); comm_init_external(ctx, rank, world_size, allgather, user); });
+}
+
 int mgvib200_model_create(mgvib200_ctx* ctx, const mgvib200_model_desc* d, mgvib200_model** out) {
     if (!ctx || !d || !out) return MGVIB200_ERR_INVALID;
     *out = nullptr;
@@ -317,6 +377,7 @@ void mgvib200_model_destroy(mgvib200_model* m) {
     if (!m) return;
     delete m->eng;
     for (auto& s : m->stage) s.release();
+    m->obj_R.release();
     delete m;
 }
 
@@ -488,6 +549,56 @@ int mgvib200_newtoncg(mgvib200_model* m, const double* x0, const double* R, int6
         double* od = stage_out(m, 6, nt);
         newtoncg_dev(m, xd, rd, n, ncg_defaults(opts), od, f, trace);
         rt_d2h(x, od, sizeof(double) * nt, m->ctx->stream);
+        rt_sync(m->ctx->stream);
+    });
+}
+
+int mgvib200_objective_bind(mgvib200_model* m, const double* R, int64_t n) {
+    if (!m || !R) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        need(n >= 1, "objective_bind: n must be >= 1");
+        rt_set_device(m->ctx->device);
+        const size_t cnt = (size_t)m->eng->n_theta * n;
+        m->obj_R.ensure(sizeof(double) * cnt);
+        rt_h2d(m->obj_R.p, R, sizeof(double) * cnt, m->ctx->stream);
+        rt_sync(m->ctx->stream);
+        m->obj_n = n;
+    });
+}
+
+int mgvib200_objective_eval(mgvib200_model* m, const double* x, double* f, double* grad) {
+    if (!m || !x || !f) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        need(m->obj_n >= 1, "objective_eval: call mgvib200_objective_bind first");
+        rt_set_device(m->ctx->device);
+        const size_t nt = (size_t)m->eng->n_theta;
+        double* xd = stage_in(m, 0, x, nt);
+        double* gd = grad ? stage_out(m, 5, nt) : nullptr;
+        *f = m->eng->kl_value_grad(xd, m->obj_R.as<double>(), m->obj_n, gd);
+        if (grad) rt_d2h(grad, gd, sizeof(double) * nt, m->ctx->stream);
+        rt_sync(m->ctx->stream);
+    });
+}
+
+int mgvib200_newton_probe(mgvib200_model* m, const double* x_n, const double* R, int64_t n,
+                          const mgvib200_newtoncg_opts* opts, mgvib200_probe_rec* probe) {
+    if (!m || !x_n || !R || !probe) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        need(n >= 1, "newton_probe: n must be >= 1");
+        need(probe->step >= 1 && probe->step <= MGVIB200_TRACE_MAX, "newton_probe: step must be in [1, 64]");
+        need(probe->max_rec >= 0 && probe->force_k >= 0, "newton_probe: max_rec and force_k must be >= 0");
+        rt_set_device(m->ctx->device);
+        const size_t nt = (size_t)m->eng->n_theta;
+        double* xd = stage_in(m, 0, x_n, nt);
+        double* rd = stage_in(m, 3, R, nt * n);
+        m->ctx->nw_x.ensure(sizeof(double) * nt);
+        double* x = m->ctx->nw_x.as<double>();
+        rt_d2d(x, xd, sizeof(double) * nt, m->ctx->stream);
+        mgvib200_newtoncg_trace tr;
+        memset(&tr, 0, sizeof tr);
+        probe->n_ls = 0;
+        double f_prev = probe->f_prev, df_n = probe->df_n, f_n = 0.0;
+        newton_one_step(m, x, rd, n, ncg_defaults(opts), probe->step, f_prev, df_n, f_n, tr, probe);
         rt_sync(m->ctx->stream);
     });
 }

@@ -166,7 +166,16 @@ struct DenseEngine : Engine {
     bool ncg_first = true, have_chol = false;
     int h_act = 0;
 
+    bool counted = false;
+    // "replicas only" (SURVEY.md 8e): mgvib200_comm_init refuses contexts that hold a dense model, setup()
+    // refuses a context that already has a communicator; this covers every entry point that would sum
+    // over residual samples
+    void single_rank_only() const {
+        if (ctx->world > 1) throw RtError{"DENSE_LINEAR: replicas only (SURVEY.md 8e); run one replica per GPU", 3};
+    }
+
     ~DenseEngine() override {
+        if (counted) ctx->n_models_single_rank--;
         DevBuf* all[] = {&J, &data, &M, &h, &center, &Mf, &W, &P2, &MP, &gsum, &ws_r, &ws_p, &ws_t, &n_x, &n_r, &n_p,
                          &n_t, &Rinv, &rws.partials, &rws.counters, &rws.red};
         for (auto* b : all) b->release();
@@ -366,6 +375,7 @@ struct DenseEngine : Engine {
     }
 
     double kl_value_grad(const double* x, const double* R, int64_t n, double* grad) override {
+        single_rank_only();
         const int np = (int)(2 * n);
         P2.ensure(8 * (size_t)k * np); MP.ensure(8 * (size_t)k * np); gsum.ensure(8 * k);
         vec_build_samples(ctx, rws, x, R, k, (int)n, P2.as<double>());          // points x +- r_i
@@ -385,7 +395,7 @@ struct DenseEngine : Engine {
         return tot / (double)np + 0.5 * dd + const_term;
     }
 
-    void mean_metric_prepare(const double*, const double*, int64_t) override {}   // M does not depend on the point
+    void mean_metric_prepare(const double*, const double*, int64_t) override { single_rank_only(); }   // M does not depend on the point
     void mean_metric_apply(const double* u, double* out) override { apply_M(u, 1, out); }
 
     void ncg_init(const double* g) override {
@@ -416,6 +426,12 @@ struct DenseEngine : Engine {
         ncg_first = false;
     }
     const double* ncg_dx() override { return n_x.as<double>(); }
+    double ncg_residual() override {
+        double h = 0.0;
+        rt_d2h(&h, ncgws.rnorm.p, sizeof(double), ctx->stream);
+        rt_sync(ctx->stream);
+        return h;
+    }
 };
 
 }  // namespace
@@ -429,6 +445,8 @@ Engine* make_dense_engine(mgvib200_ctx* ctx, const mgvib200_model_desc& d) {
         delete e;
         throw;
     }
+    ctx->n_models_single_rank++;
+    e->counted = true;
     return e;
 }
 

@@ -52,6 +52,9 @@ struct mgvib200_ctx {
     // per-context device scratch of the model-independent drivers (Newton-CG, mgvi_step): owned by the
     // context so that several contexts (devices) can live in one process
     mgvi::DevBuf nw_x, nw_g, nw_trial, nw_gt, nw_zero, step_R, count_scalar;
+    // multi-GPU bookkeeping (comm.cu): cached global residual count, models that cannot be sharded
+    int64_t n_cache_local = -1, n_cache_glob = -1;
+    int n_models_single_rank = 0;
     mgvi::ReduceWs drv_rws;
     // per-kernel timing (bench.py roofline): CUDA events around every launch while enabled
     bool profile = false;
@@ -118,6 +121,9 @@ struct Engine {
     virtual bool ncg_active() = 0;          // iterator would yield another update
     virtual void ncg_update() = 0;          // one CG update (dx += alpha u ...)
     virtual const double* ncg_dx() = 0;     // current dx (device)
+    // parity probe (mgvib200_newton_probe): residual norm of the inner CG, mean metric weight (host copy)
+    virtual double ncg_residual() { return NAN; }
+    virtual void get_mean_weights(double*) { throw RtError{"the mean metric weight is only exposed by FIELD_DHT models", 3}; }
 };
 
 Engine* make_field_engine(mgvib200_ctx* ctx, const mgvib200_model_desc& d);
@@ -125,8 +131,17 @@ Engine* make_poly_engine(mgvib200_ctx* ctx, const mgvib200_model_desc& d);
 Engine* make_dense_engine(mgvib200_ctx* ctx, const mgvib200_model_desc& d);
 
 // communicator (comm.cu)
-void comm_allreduce_sum(mgvib200_ctx* ctx, double* dev, long long count);
+void comm_allgather(mgvib200_ctx* ctx, const double* send_dev, double* recv_dev, long long count_per_rank);
 int64_t comm_global_count(mgvib200_ctx* ctx, int64_t local);
+
+// Canonical summation order over residual samples, independent of the number of ranks: the n_glob
+// samples are cut into `chunks` = gcd(n_glob, 8) contiguous chunks of `per_chunk` samples; a sum
+// over samples is  sum_c ( sum_{i in chunk c} term_i ), both levels sequential in index order.
+// Rank g of W (W in {1, 2, 4, 8}) owns the contiguous chunks [g chunks/W, (g+1) chunks/W).
+struct CanonShape {
+    int64_t n_glob = 0, chunks = 1, per_chunk = 0, chunks_local = 1;
+};
+CanonShape canon_shape(mgvib200_ctx* ctx, int64_t n_local);
 
 // generic vector helpers (vec_host.cu)
 void vec_launch(mgvib200_ctx* ctx, ReduceWs& ws, VecParams P);
@@ -138,6 +153,13 @@ void vec_build_samples(mgvib200_ctx* ctx, ReduceWs& ws, const double* c, const d
                        double* samples);
 void vec_sum_chunks(mgvib200_ctx* ctx, ReduceWs& ws, const double* in, long long ld, int nsum, double scale,
                     double* out, long long N);
+// out = scale * (canonical sum over all ranks' terms) ; in = [terms_local][N] with `terms_per_sample`
+// consecutive terms per residual sample (2 for the +/- points, 1 for the '+' points)
+void vec_canon_sum(mgvib200_ctx* ctx, ReduceWs& ws, const CanonShape& cs, const double* in, long long ld,
+                   int terms_per_sample, double scale, double* out, long long N, DevBuf& gather);
+// canonical sum of per-term scalars: `groups` arrays of `count` doubles each, laid out back to back at
+// dev (local values); returns the sum over all ranks, group after group, each in global term order
+double canon_scalar_sum(mgvib200_ctx* ctx, DevBuf& gather, const double* dev_local, int groups, long long count);
 void vec_cg_init(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, const double* b, long long b_ld, double* x,
                  double* r, double* p, long long N, int nvec);
 void vec_cg_update(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* x, double* r, const double* p,
@@ -150,4 +172,6 @@ struct mgvib200_model {
     mgvi::Engine* eng = nullptr;
     mgvi::DevBuf stage[8];      // host-pointer API staging buffers
     bool linearized = false;
+    mgvi::DevBuf obj_R;         // residual samples bound by mgvib200_objective_bind
+    int64_t obj_n = 0;
 };

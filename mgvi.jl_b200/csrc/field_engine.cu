@@ -60,8 +60,8 @@ struct FieldEngine : Engine {
     CgWs cgws, ncgws;
     DevBuf ws_r, ws_p, ws_t;          // sampler CG vectors [nvec][N]
     DevBuf pt_t;                      // per-point scratch [npoints][N]
-    DevBuf acc;                       // chunk accumulators
-    DevBuf qsum;                      // N + 2
+    DevBuf gather, sc_gather, kl_red; // canonical sums: gathered chunk partials [chunks][N], per-point scalars
+    DevBuf qsum;                      // N
     DevBuf n_x, n_r, n_p, n_t;        // Newton CG state (single vector)
     DevBuf tmpA, tmpB;                // generic-path staging [nvec][N]
     CgScalars ncg_sc;
@@ -69,7 +69,7 @@ struct FieldEngine : Engine {
     int h_ncg[2] = {0, 0};
 
     ~FieldEngine() override {
-        DevBuf* all[] = {&A, &data, &w, &q, &wbar, &center, &w_tiled, &ws_tile, &ws_r, &ws_p, &ws_t, &pt_t, &acc, &qsum, &n_x, &n_r,
+        DevBuf* all[] = {&A, &data, &w, &q, &wbar, &center, &w_tiled, &ws_tile, &ws_r, &ws_p, &ws_t, &pt_t, &gather, &sc_gather, &kl_red, &qsum, &n_x, &n_r,
                          &n_p, &n_t, &tmpA, &tmpB, &rws.partials, &rws.counters, &rws.red};
         for (auto* b : all) b->release();
         for (auto& kv : tw) kv.second.release();
@@ -132,7 +132,7 @@ struct FieldEngine : Engine {
         q.ensure(sizeof(double) * N);
         wbar.ensure(sizeof(double) * N);
         center.ensure(sizeof(double) * N);
-        qsum.ensure(sizeof(double) * (N + 2));
+        qsum.ensure(sizeof(double) * N);
         // constants of the objective: Distributions.jl logpdf normalisers + prior (src/mgvi_impl.jl:3-7)
         double cl = 0.0;
         if (like == LIKE_POISSON) {
@@ -209,7 +209,7 @@ struct FieldEngine : Engine {
     // long 1-D fields (big1d_pass.h)
     // ------------------------------------------------------------------------------------------
     template <int KIND, int PRO, int EPI>
-    long long launch_big(FieldPassParams P, int nvec, bool accumulate) {
+    void launch_big(FieldPassParams P, int nvec) {
         BigParams B;
         memset(&B, 0, sizeof B);
         const int npairs = (nvec + 1) / 2;
@@ -230,13 +230,11 @@ struct FieldEngine : Engine {
         G = std::max<long long>(G, (32 + upt - 1) / upt);
         B.G = (int)G;
         B.npairs = npairs;
-        int npgrp = npairs;
+        const int npgrp = npairs;
         B.nloop = 1;
-        if (accumulate) { npgrp = std::min(npairs, 8); B.nloop = (npairs + npgrp - 1) / npgrp; npgrp = (npairs + B.nloop - 1) / B.nloop; }
         const long long ubl = (B.units_per_pair + G - 1) / G;
         const long long grid = ubl * npgrp;
         P.N = N; P.nvec = nvec;
-        if (accumulate) { acc.ensure(sizeof(double) * N * npgrp); P.acc_out = acc.as<double>(); }
         if (P.fin != FIN_NONE) {
             const size_t np = (P.fin == FIN_TOTAL) ? (size_t)grid : (size_t)(nvec + 1) * (size_t)ubl;
             reduce_ws_ensure(rws, ctx, np, (size_t)nvec + 1);
@@ -248,7 +246,6 @@ struct FieldEngine : Engine {
         rt_launch(k_big1d<KIND, PRO, EPI>, grid, (int)(G * upt), smem, ctx->stream, B);
         ctx->prof_post();
         ctx->launches++;
-        return npgrp;
     }
 
     // ------------------------------------------------------------------------------------------
@@ -391,23 +388,6 @@ struct FieldEngine : Engine {
         ctx->launches++;
     }
 
-    // number of chunk accumulators a looping last pass will write
-    long long acc_chunks(const PassGeo& g, int nvec, int& nsgrp, int& nloop) const {
-        if (g.geo == GEO_PAIRVEC) {
-            const long long npairs = (nvec + 1) / 2;
-            // aim for a handful of blocks; every unit accumulates its own pairs
-            long long blocks = std::min<long long>(8, (npairs + g.G - 1) / g.G);
-            blocks = std::max<long long>(blocks, 1);
-            nloop = (int)((npairs + blocks * g.G - 1) / (blocks * g.G));
-            nsgrp = 1;
-            const long long grid = (npairs + (long long)g.G * nloop - 1) / ((long long)g.G * nloop);
-            return grid * g.G;
-        }
-        nsgrp = std::min(nvec, 8);
-        nloop = (nvec + nsgrp - 1) / nsgrp;
-        return nsgrp;
-    }
-
     // ------------------------------------------------------------------------------------------
     // generic (any length) chain pieces
     // ------------------------------------------------------------------------------------------
@@ -427,7 +407,7 @@ struct FieldEngine : Engine {
 
     template <int PRO, int EPI>
     void chain_generic(FieldPassParams P, int nvec, bool metric, int fin_pro, double* red_pro, int fin_epi,
-                       double* red_epi, bool accumulate) {
+                       double* red_epi) {
         tmpA.ensure(sizeof(double) * N * nvec);
         tmpB.ensure(sizeof(double) * N * nvec);
         double* cur = tmpA.as<double>();
@@ -436,7 +416,7 @@ struct FieldEngine : Engine {
         P.N = N; P.nvec = nvec;
         {
             ElemParams E;
-            E.f = P; E.tmp = cur; E.total = (long long)nvec * N; E.nloop_all = 0;
+            E.f = P; E.tmp = cur; E.total = (long long)nvec * N;
             E.f.fin = fin_pro; E.f.red_out = red_pro;
             const long long grid = nchunk * nvec;
             if (fin_pro != FIN_NONE) {
@@ -450,9 +430,9 @@ struct FieldEngine : Engine {
         if (metric) naive_transform_all(cur, other, nvec, nullptr);
         {
             ElemParams E;
-            E.f = P; E.tmp = cur; E.total = (long long)nvec * N; E.nloop_all = accumulate ? 1 : 0;
+            E.f = P; E.tmp = cur; E.total = (long long)nvec * N;
             E.f.fin = fin_epi; E.f.red_out = red_epi;
-            const long long grid = accumulate ? nchunk : nchunk * nvec;
+            const long long grid = nchunk * nvec;
             if (fin_epi != FIN_NONE) {
                 reduce_ws_ensure(rws, ctx, (size_t)grid, (size_t)std::max(nvec, 1));
                 E.f.partials = rws.partials.as<double>(); E.f.counters = rws.counters.as<unsigned>();
@@ -463,39 +443,32 @@ struct FieldEngine : Engine {
     }
 
     // ------------------------------------------------------------------------------------------
-    // chains.  `scratch` is [nvec][N].  Returns the number of chunk accumulators written
-    // (accumulate mode) or 0.
+    // chains.  `scratch` is [nvec][N].  Per-vector reductions: fin_pro over the prologue terms (first
+    // pass), fin_epi over the epilogue terms (last pass); single-pass geometries put both into the
+    // fin_epi slots.
     // ------------------------------------------------------------------------------------------
     template <int PRO, int EPI>
-    long long chain_forward(FieldPassParams P, int nvec, double* scratch, int fin_pro, double* red_pro, int fin_epi,
-                            double* red_epi, bool accumulate) {
+    void chain_forward(FieldPassParams P, int nvec, double* scratch, int fin_pro, double* red_pro, int fin_epi,
+                       double* red_epi) {
         P.scale = c * pow(0.5, ndim);
         if (!fast) {
-            if (accumulate) { acc.ensure(sizeof(double) * N); P.acc_out = acc.as<double>(); }
-            chain_generic<PRO, EPI>(P, nvec, false, fin_pro, red_pro, fin_epi, red_epi, accumulate);
-            return accumulate ? 1 : 0;
+            chain_generic<PRO, EPI>(P, nvec, false, fin_pro, red_pro, fin_epi, red_epi);
+            return;
         }
         if (big) {
             FieldPassParams Q = P;
-            Q.fin = fin_pro; Q.red_out = red_pro; Q.acc_out = nullptr;
-            launch_big<BIG_A, PRO, EPI_STORE>(Q, nvec, false);
+            Q.fin = fin_pro; Q.red_out = red_pro;
+            launch_big<BIG_A, PRO, EPI_STORE>(Q, nvec);
             FieldPassParams E = P;
             E.fin = fin_epi; E.red_out = red_epi; E.data = data_perm.as<double>();
-            return launch_big<BIG_B_END, PRO_LOAD, EPI>(E, nvec, accumulate);
+            launch_big<BIG_B_END, PRO_LOAD, EPI>(E, nvec);
+            return;
         }
         if (ndim == 1) {
-            PassGeo g = geo_axis(0, nvec);
-            int nsgrp = 1, nloop = 1;
-            long long chunks = 0;
-            if (accumulate) {
-                chunks = acc_chunks(g, nvec, nsgrp, nloop);
-                acc.ensure(sizeof(double) * N * chunks);
-                P.acc_out = acc.as<double>();
-            }
             P.fin = (fin_epi != FIN_NONE) ? fin_epi : fin_pro;
             P.red_out = (fin_epi != FIN_NONE) ? red_epi : red_pro;
-            launch_pass<GEO_PAIRVEC, PRO, EPI, false>(P, g, nvec, nsgrp, nloop);
-            return chunks;
+            launch_pass<GEO_PAIRVEC, PRO, EPI, false>(P, geo_axis(0, nvec), nvec, 1, 1);
+            return;
         }
         // contiguous axis first
         {
@@ -511,32 +484,23 @@ struct FieldEngine : Engine {
         {
             FieldPassParams Q = P;
             Q.in = scratch; Q.in_ld = N; Q.fin = fin_epi; Q.red_out = red_epi;
-            PassGeo g = geo_axis(0, nvec);
-            int nsgrp = nvec, nloop = 1;
-            long long chunks = 0;
-            if (accumulate) {
-                chunks = acc_chunks(g, nvec, nsgrp, nloop);
-                acc.ensure(sizeof(double) * N * chunks);
-                Q.acc_out = acc.as<double>();
-            }
-            launch_pass<GEO_STRIDED, PRO_LOAD, EPI, false>(Q, g, nvec, nsgrp, nloop);
-            return chunks;
+            launch_pass<GEO_STRIDED, PRO_LOAD, EPI, false>(Q, geo_axis(0, nvec), nvec, nvec, 1);
         }
     }
 
     template <int PRO, int EPI>
     void chain_adjoint(FieldPassParams P, int nvec, double* scratch, int fin_epi, double* red_epi) {
         if (!fast) {
-            chain_generic<PRO, EPI>(P, nvec, false, FIN_NONE, nullptr, fin_epi, red_epi, false);
+            chain_generic<PRO, EPI>(P, nvec, false, FIN_NONE, nullptr, fin_epi, red_epi);
             return;
         }
         if (big) {
             FieldPassParams Q = P;
             Q.fin = FIN_NONE;
-            launch_big<BIG_B_START, PRO, EPI_STORE>(Q, nvec, false);
+            launch_big<BIG_B_START, PRO, EPI_STORE>(Q, nvec);
             FieldPassParams E = P;
             E.fin = fin_epi; E.red_out = red_epi;
-            launch_big<BIG_AP, PRO_LOAD, EPI>(E, nvec, false);
+            launch_big<BIG_AP, PRO_LOAD, EPI>(E, nvec);
             return;
         }
         if (ndim == 1) {
@@ -566,17 +530,17 @@ struct FieldEngine : Engine {
     void chain_metric(FieldPassParams P, int nvec, double* scratch, int fin, double* red) {
         P.scale = c * c * pow(0.5, 2 * ndim);
         if (!fast) {
-            chain_generic<PRO, EPI_METRIC>(P, nvec, true, FIN_NONE, nullptr, fin, red, false);
+            chain_generic<PRO, EPI_METRIC>(P, nvec, true, FIN_NONE, nullptr, fin, red);
             return;
         }
         if (big) {
             FieldPassParams Q = P;
             Q.fin = FIN_NONE;
-            launch_big<BIG_A, PRO, EPI_STORE>(Q, nvec, false);
-            launch_big<BIG_B_MID, PRO_LOAD, EPI_STORE>(Q, nvec, false);
+            launch_big<BIG_A, PRO, EPI_STORE>(Q, nvec);
+            launch_big<BIG_B_MID, PRO_LOAD, EPI_STORE>(Q, nvec);
             FieldPassParams E = P;
             E.fin = fin; E.red_out = red;
-            launch_big<BIG_AP, PRO_LOAD, EPI_METRIC>(E, nvec, false);
+            launch_big<BIG_AP, PRO_LOAD, EPI_METRIC>(E, nvec);
             return;
         }
         if (ndim == 1) {
@@ -630,6 +594,14 @@ struct FieldEngine : Engine {
         }
     }
 
+    // 1-D fields pack TWO residual samples into one complex transform (fft_core.h), so a sample's rounding
+    // depends on its partner: with an odd number of residuals per rank the partners would depend on the
+    // sharding.  Refused rather than silently rank-count dependent.
+    void check_pairing(int64_t n_local) const {
+        if (ctx->world > 1 && ndim == 1 && fast && (n_local & 1))
+            throw RtError{"multi-GPU, 1-D field: every rank needs an even number of residual samples", 1};
+    }
+
     FieldPassParams base_params() const {
         FieldPassParams P;
         memset(&P, 0, sizeof P);
@@ -651,7 +623,7 @@ struct FieldEngine : Engine {
         P.x = x; P.point_mode = POINT_CENTER;
         P.w_out = w.as<double>(); P.q_out = q.as<double>();
         pt_t.ensure(sizeof(double) * N);
-        chain_forward<PRO_POINT, EPI_LINEARIZE>(P, 1, pt_t.as<double>(), FIN_NONE, nullptr, FIN_NONE, nullptr, false);
+        chain_forward<PRO_POINT, EPI_LINEARIZE>(P, 1, pt_t.as<double>(), FIN_NONE, nullptr, FIN_NONE, nullptr);
         rt_d2d(center.p, x, sizeof(double) * N, ctx->stream);
         ++w_gen;
     }
@@ -660,17 +632,9 @@ struct FieldEngine : Engine {
         if (w_host) rt_d2h(w_host, w.p, sizeof(double) * N, ctx->stream);
         if (q_host) rt_d2h(q_host, q.p, sizeof(double) * N, ctx->stream);
         rt_sync(ctx->stream);
-        if (big) {
-            // device order is the permuted data-space order [k1][k2] <-> k = k1 + n1 k2
-            const long long n1 = 1LL << lg_n1, n2 = 1LL << lg_n2;
-            std::vector<double> t(N);
-            for (double* arr : {w_host, q_host}) {
-                if (!arr) continue;
-                for (long long r = 0; r < n1; ++r)
-                    for (long long cc = 0; cc < n2; ++cc) t[r + n1 * cc] = arr[r * n2 + cc];
-                memcpy(arr, t.data(), sizeof(double) * N);
-            }
-        }
+        if (big)
+            for (double* arr : {w_host, q_host})
+                if (arr) unpermute_big(arr);
     }
 
     void metric_apply(const double* V, int64_t k, double* MV) override {
@@ -682,6 +646,7 @@ struct FieldEngine : Engine {
 
     void sample_cg(const double* Z1, const double* Z2, int64_t n, const mgvib200_cg_opts& o, double* R,
                    int64_t* iters_host, double* rnorm_host) override {
+        check_pairing(n);
         const int nvec = (int)n;
         const size_t vb = sizeof(double) * N * nvec;
         ws_r.ensure(vb); ws_p.ensure(vb); ws_t.ensure(vb);
@@ -746,44 +711,41 @@ struct FieldEngine : Engine {
 
     double kl_value_grad(const double* x, const double* R, int64_t n, double* grad) override {
         const int npoints = (int)(2 * n);
-        const int64_t n_glob = comm_global_count(ctx, n);
-        reduce_ws_ensure(rws, ctx, 1, 1);
-        double* red = rws.red.as<double>();
-        rt_memset(red, 0, sizeof(double) * 2, ctx->stream);
+        const CanonShape cs = canon_shape(ctx, n);
+        // per-point scalars: [prior term 1/2 |p|^2 (npoints)] [variable part of -loglike (npoints)]
+        kl_red.ensure(sizeof(double) * 2 * npoints);
+        double* red = kl_red.as<double>();
+        rt_memset(red, 0, sizeof(double) * 2 * npoints, ctx->stream);
         pt_t.ensure(sizeof(double) * N * npoints);
         FieldPassParams P = base_params();
         P.x = x; P.R = R; P.R_ld = N; P.point_mode = POINT_PM; P.want_grad = grad ? 1 : 0;
-        const long long chunks = chain_forward<PRO_POINT, EPI_KL>(P, npoints, pt_t.as<double>(), FIN_TOTAL, red,
-                                                                  FIN_TOTAL, red + 1, grad != nullptr);
-        double* qs = qsum.as<double>();
-        if (grad) vec_sum_chunks(ctx, rws, acc.as<double>(), N, (int)chunks, 1.0, qs, N);
-        rt_d2d(qs + N, red, sizeof(double) * 2, ctx->stream);
-        if (grad) comm_allreduce_sum(ctx, qs, N + 2);
-        else comm_allreduce_sum(ctx, qs + N, 2);
-        double hf[2];
-        rt_d2h(hf, qs + N, sizeof(double) * 2, ctx->stream);
-        rt_sync(ctx->stream);
+        // per-point gradient inputs g'(s_p) dl/dlambda(p) land in the scratch itself (the last pass writes
+        // the positions it read)
+        P.out = pt_t.as<double>(); P.out_ld = N;
+        chain_forward<PRO_POINT, EPI_KL>(P, npoints, pt_t.as<double>(), FIN_VEC_STORE, red, FIN_VEC_STORE, red + npoints);
+        // sums over the residual samples in the canonical, sharding-independent order (engine.h)
+        const double ftot = canon_scalar_sum(ctx, sc_gather, red, 2, npoints);
         if (grad) {
+            double* qs = qsum.as<double>();
+            vec_canon_sum(ctx, rws, cs, pt_t.as<double>(), N, 2, 1.0, qs, N, gather);
             // grad = x - (1/2n) c A . H( sum_p g'(s_p) dl/dlambda(p) )
             FieldPassParams Q = base_params();
             Q.in = qs; Q.in_ld = N; Q.x = x; Q.out = grad;
-            Q.scale = c * pow(0.5, ndim) / (2.0 * (double)n_glob);
+            Q.scale = c * pow(0.5, ndim) / (2.0 * (double)cs.n_glob);
             chain_adjoint<PRO_LOAD, EPI_GRAD>(Q, 1, pt_t.as<double>(), FIN_NONE, nullptr);
         }
-        return (hf[0] + hf[1]) / (2.0 * (double)n_glob) + const_term;
+        return ftot / (2.0 * (double)cs.n_glob) + const_term;
     }
 
     void mean_metric_prepare(const double* x, const double* R, int64_t n) override {
-        const int64_t n_glob = comm_global_count(ctx, n);
+        check_pairing(n);
+        const CanonShape cs = canon_shape(ctx, n);
         pt_t.ensure(sizeof(double) * N * n);
         FieldPassParams P = base_params();
         P.x = x; P.R = R; P.R_ld = N; P.point_mode = POINT_PLUS;
-        acc.ensure(sizeof(double) * N);
-        P.acc_out = acc.as<double>();     // non-null selects accumulation; chain_forward re-points it
-        const long long chunks = chain_forward<PRO_POINT, EPI_LINEARIZE>(P, (int)n, pt_t.as<double>(), FIN_NONE,
-                                                                         nullptr, FIN_NONE, nullptr, true);
-        vec_sum_chunks(ctx, rws, acc.as<double>(), N, (int)chunks, 1.0 / (double)n_glob, wbar.as<double>(), N);
-        comm_allreduce_sum(ctx, wbar.as<double>(), N);
+        P.out = pt_t.as<double>(); P.out_ld = N;      // per-sample weights w_i = F g'^2 at x + r_i
+        chain_forward<PRO_POINT, EPI_LINEARIZE>(P, (int)n, pt_t.as<double>(), FIN_NONE, nullptr, FIN_NONE, nullptr);
+        vec_canon_sum(ctx, rws, cs, pt_t.as<double>(), N, 1, 1.0 / (double)cs.n_glob, wbar.as<double>(), N, gather);
         ++w_gen;
     }
 
@@ -827,6 +789,28 @@ struct FieldEngine : Engine {
     }
 
     const double* ncg_dx() override { return n_x.as<double>(); }
+
+    double ncg_residual() override {
+        double h = 0.0;
+        rt_d2h(&h, ncgws.rnorm.p, sizeof(double), ctx->stream);
+        rt_sync(ctx->stream);
+        return h;
+    }
+
+    void unpermute_big(double* arr) const {
+        // device order is the permuted data-space order [k1][k2] <-> k = k1 + n1 k2
+        const long long n1 = 1LL << lg_n1, n2 = 1LL << lg_n2;
+        std::vector<double> t(N);
+        for (long long r = 0; r < n1; ++r)
+            for (long long cc = 0; cc < n2; ++cc) t[r + n1 * cc] = arr[r * n2 + cc];
+        memcpy(arr, t.data(), sizeof(double) * N);
+    }
+
+    void get_mean_weights(double* w_host) override {
+        rt_d2h(w_host, wbar.p, sizeof(double) * N, ctx->stream);
+        rt_sync(ctx->stream);
+        if (big) unpermute_big(w_host);
+    }
 };
 
 }  // namespace

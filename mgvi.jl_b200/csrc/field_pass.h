@@ -63,8 +63,7 @@ struct FieldPassParams {
     const double* Z2;  long long Z2_ld;
     double* r; double* p; double* xout;       // CG vectors (leading dimension N)
     const double* data;                       // observations (N)
-    double* w_out; double* q_out; double* lam_out;
-    double* acc_out;                          // [nchunk][N] accumulators (gradient input / mean weight)
+    double* w_out; double* q_out; double* lam_out;   // EPI_LINEARIZE at the centre (out == null)
     double scale, offset, sigma, inv_sigma2;
     int link, likelihood, first_iter, want_grad;
     int mask_active;                          // skip vectors whose cg.active flag is 0 (CG iterations only)
@@ -173,10 +172,12 @@ SIMT_DEVICE double2 pro_pair(const FieldPassParams& P, int sa, int sb, long long
     }
 }
 
-// accv: per-element accumulators across the vector loop (gradient input / mean weight)
+// Per-point fields (the gradient input g' dl/dlambda of EPI_KL, the metric weight of EPI_LINEARIZE away
+// from the centre) are STORED per vector; sums over residual samples are formed afterwards in the
+// canonical order (vec_ops.h: VOP_SUM_CANON) so that they do not depend on the sharding.
 template <int EPI>
 SIMT_DEVICE void epi_pair(const FieldPassParams& P, int sa, int sb, long long pa, long long pb, bool va,
-                          bool vb, bool adj, double2 val, double& acc_a, double& acc_b, double2& accv) {
+                          bool vb, bool adj, double2 val, double& acc_a, double& acc_b) {
     if (EPI == EPI_STORE) {
         st_pair(P.out, sa * P.out_ld + pa, sb * P.out_ld + pb, va, vb, adj, val);
     } else if (EPI == EPI_METRIC) {
@@ -190,8 +191,8 @@ SIMT_DEVICE void epi_pair(const FieldPassParams& P, int sa, int sb, long long pa
         double wa = 0, qa = 0, la = 0, wb = 0, qb = 0, lb = 0;
         if (va) lin_point(P, P.scale * val.x + P.offset, wa, qa, la);
         if (vb) lin_point(P, P.scale * val.y + P.offset, wb, qb, lb);
-        if (P.acc_out) {
-            accv.x += wa; accv.y += wb;
+        if (P.out) {
+            st_pair(P.out, sa * P.out_ld + pa, sb * P.out_ld + pb, va, vb, adj, make_double2(wa, wb));
         } else {
             st_pair(P.w_out, pa, pb, va, vb, adj, make_double2(wa, wb));
             st_pair(P.q_out, pa, pb, va, vb, adj, make_double2(qa, qb));
@@ -213,7 +214,7 @@ SIMT_DEVICE void epi_pair(const FieldPassParams& P, int sa, int sb, long long pa
         if (va) kl_point(P, P.scale * val.x + P.offset, d.x, na, qa);
         if (vb) kl_point(P, P.scale * val.y + P.offset, d.y, nb, qb);
         acc_a += na; acc_b += nb;
-        accv.x += qa; accv.y += qb;
+        if (P.want_grad) st_pair(P.out, sa * P.out_ld + pa, sb * P.out_ld + pb, va, vb, adj, make_double2(qa, qb));
     } else {  // EPI_GRAD: grad = x - scale * A . val   (scale carries c / (2n) and the 1/2 factors)
         double2 xv = ldg_pair(P.x, pa, pb, va, vb, adj);
         double2 a = ldg_pair(P.A, pa, pb, va, vb, adj);
@@ -495,11 +496,6 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
     }
 
     double acc_a = 0.0, acc_b = 0.0;
-    double2 accv[8];
-    if (EPI == EPI_KL || EPI == EPI_LINEARIZE) {
-#pragma unroll
-        for (int m = 0; m < 8; ++m) accv[m] = make_double2(0.0, 0.0);
-    }
     // element offsets of my 8 elements: off_a + m * step (and off_b + m * step)
     unsigned off_a = 0, off_b = 0, step = (unsigned)n8;
     bool unit_ok = true;
@@ -657,7 +653,7 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
             if (pairvec) {
 #pragma unroll
                 for (int m = 0; m < 8; ++m)
-                    epi_pair<EPI>(P, sa, sb, off_a + m * step, off_b + m * step, va, vb, false, v[m], acc_a, acc_b, accv[m]);
+                    epi_pair<EPI>(P, sa, sb, off_a + m * step, off_b + m * step, va, vb, false, v[m], acc_a, acc_b);
             } else if (EPI == EPI_METRIC && staged) {
                 SIMT_MBAR_WAIT(mbar, 0);
                 epi_metric_block_staged(v, P.out, stg, P.A, off_a, off_b, step, (long long)sa * P.out_ld, lt, 1 << log2n,
@@ -679,22 +675,10 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
 #pragma unroll
                 for (int m = 0; m < 8; ++m)
                     if (EPI == EPI_STORE)
-                        epi_pair<EPI>(P, sa, sb, toff_a + m * tstep, toff_b + m * tstep, true, true, adj, v[m], acc_a, acc_b, accv[m]);
+                        epi_pair<EPI>(P, sa, sb, toff_a + m * tstep, toff_b + m * tstep, true, true, adj, v[m], acc_a, acc_b);
                     else
-                        epi_pair<EPI>(P, sa, sb, off_a + m * step, off_b + m * step, true, true, adj, v[m], acc_a, acc_b, accv[m]);
+                        epi_pair<EPI>(P, sa, sb, off_a + m * step, off_b + m * step, true, true, adj, v[m], acc_a, acc_b);
             }
-        }
-    }
-    // ---- accumulated per-element outputs ---------------------------------------------------
-    if ((EPI == EPI_KL && P.want_grad) || (EPI == EPI_LINEARIZE && P.acc_out != nullptr)) {
-        if (pairvec) {
-            const long long chunk = bt * P.G + g;
-#pragma unroll
-            for (int m = 0; m < 8; ++m) P.acc_out[chunk * P.N + off_a + m * step] = accv[m].x + accv[m].y;
-        } else if (unit_ok) {
-#pragma unroll
-            for (int m = 0; m < 8; ++m)
-                st_pair(P.acc_out + (long long)sgrp * P.N, off_a + m * step, off_b + m * step, true, true, adj, accv[m]);
         }
     }
     // ---- scalar reductions -----------------------------------------------------------------
@@ -726,8 +710,7 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
 struct ElemParams {
     FieldPassParams f;
     double* tmp;           // [nvec][N] staging values
-    long long total;       // nvec * N (pro) or N (epi with loop)
-    int nloop_all;         // epi: loop over all nvec vectors per element (accumulating modes)
+    long long total;       // nvec * N
 };
 
 template <int PRO>
@@ -763,25 +746,6 @@ SIMT_DEVICE void elem_epi_body(const ElemParams& E, unsigned char* smem_raw) {
     int* flag = reinterpret_cast<int*>(smem_raw + 256);
     const long long nchunk = (P.N + SIMT_NTID - 1) / SIMT_NTID;
     double acc_a = 0.0, acc_b = 0.0;
-    double2 accv = make_double2(0.0, 0.0);
-    if (E.nloop_all) {
-        // one block per pixel chunk, loops over every vector (accumulating epilogues)
-        const long long chunk = SIMT_BID;
-        const long long pix = chunk * SIMT_NTID + SIMT_TID;
-        if (pix < P.N) {
-            for (int s = 0; s < P.nvec; ++s) {
-                double2 val = make_double2(E.tmp[(long long)s * P.N + pix], 0.0);
-                epi_pair<EPI>(P, s, s, pix, pix, true, false, false, val, acc_a, acc_b, accv);
-            }
-            if ((EPI == EPI_KL && P.want_grad) || (EPI == EPI_LINEARIZE && P.acc_out != nullptr))
-                P.acc_out[pix] = accv.x;
-        }
-        if (P.fin == FIN_NONE) return;
-        const double tot = seg_reduce(acc_a, SIMT_NTID, red);
-        block_publish_and_finalize(P.fin, P.cg, P.red_out, P.partials, P.counters, 0, SIMT_BID, SIMT_NBID, tot, red,
-                                   flag);
-        return;
-    }
     const int s = (int)(SIMT_BID % P.nvec);
     const long long chunk = SIMT_BID / P.nvec;
     const long long pix = chunk * SIMT_NTID + SIMT_TID;
@@ -789,7 +753,7 @@ SIMT_DEVICE void elem_epi_body(const ElemParams& E, unsigned char* smem_raw) {
     if (use_active && !P.cg.active[s]) return;
     if (pix < P.N) {
         double2 val = make_double2(E.tmp[(long long)s * P.N + pix], 0.0);
-        epi_pair<EPI>(P, s, s, pix, pix, true, false, false, val, acc_a, acc_b, accv);
+        epi_pair<EPI>(P, s, s, pix, pix, true, false, false, val, acc_a, acc_b);
     }
     if (P.fin == FIN_NONE) return;
     const double tot = seg_reduce(acc_a, SIMT_NTID, red);

@@ -187,12 +187,15 @@ struct PolyEngine : Engine {
     long long N = 0;
     int P = 0, layout = 0;
     double ns = 60.0;
-    DevBuf x, data, cs, mu_idx, noise_idx, S, M, Mbar, center, rhs, kl, fin, n_x, n_r, n_u, n_st;
+    DevBuf x, data, cs, mu_idx, noise_idx, S, M, Mbar, center, rhs, kl, fin, n_x, n_r, n_u, n_st, cg_it, cg_rn;
     double h_st[8];
 
+    bool counted = false;
+
     ~PolyEngine() override {
+        if (counted) ctx->n_models_single_rank--;
         DevBuf* all[] = {&x, &data, &cs, &mu_idx, &noise_idx, &S, &M, &Mbar, &center, &rhs, &kl, &fin, &n_x, &n_r,
-                         &n_u, &n_st};
+                         &n_u, &n_st, &cg_it, &cg_rn};
         for (auto* b : all) b->release();
     }
 
@@ -214,6 +217,7 @@ struct PolyEngine : Engine {
     }
 
     void setup(const mgvib200_model_desc& d) {
+        single_rank_only();
         N = d.n_data; P = d.n_coef; layout = d.lambda_layout; ns = d.noise_scale;
         if (d.likelihood != MGVIB200_LIKE_NORMAL) throw RtError{"POLY: Normal likelihood only", 1};
         if (P < 1 || P + 1 > kSmallMax) throw RtError{"POLY: 1 <= n_coef <= 31", 1};
@@ -299,7 +303,8 @@ struct PolyEngine : Engine {
         p.mode = PM_RHS; p.p0 = center.as<double>(); p.Z1 = Z1; p.Z1_ld = n_lambda; p.Z2 = Z2;
         p.out = rhs.as<double>();
         launch_reduce(p, n * n_theta);
-        DevBuf it, rn;
+        DevBuf& it = cg_it;
+        DevBuf& rn = cg_rn;
         it.ensure(sizeof(int) * n); rn.ensure(8 * n);
         SmallCgParams c;
         c.M = M.as<double>(); c.B = rhs.as<double>(); c.X = R; c.iters = it.as<int>(); c.rnorm = rn.as<double>();
@@ -322,7 +327,6 @@ struct PolyEngine : Engine {
             mx = std::max<long long>(mx, hi[i]);
         }
         ctx->lockstep_iters = mx;
-        it.release(); rn.release();
     }
 
     void sample_dense(const double* Z, int64_t n, double* R, double* L) override {
@@ -332,9 +336,16 @@ struct PolyEngine : Engine {
         ctx->launches++;
     }
 
+    // single-GPU model ("replicas only"): mgvib200_comm_init refuses contexts that hold one, and a model
+    // created after comm_init is refused in setup(); the guard here covers every other ordering
+    void single_rank_only() const {
+        if (ctx->world > 1) throw RtError{"POLY: multi-GPU sharding is not provided for this latency-bound model", 3};
+    }
+
     double kl_value_grad(const double* xc, const double* R, int64_t n, double* grad) override {
+        single_rank_only();
         const int npoints = (int)(2 * n);
-        const int64_t n_glob = comm_global_count(ctx, n);
+        const int64_t n_glob = n;
         const int nq = P + 2;
         kl.ensure(8 * (size_t)npoints * nq);
         PolyParams p = base();
@@ -347,7 +358,6 @@ struct PolyEngine : Engine {
         Q.p.out = fin.as<double>(); Q.kl = kl.as<double>(); Q.mode = 0;
         rt_launch(k_poly_final, 1, 32, 0, ctx->stream, Q);
         ctx->launches++;
-        comm_allreduce_sum(ctx, fin.as<double>(), n_theta + 1);
         double hf = 0.0;
         rt_d2h(&hf, fin.p, 8, ctx->stream);
         if (grad) rt_d2d(grad, fin.as<double>() + 1, 8 * n_theta, ctx->stream);
@@ -356,12 +366,8 @@ struct PolyEngine : Engine {
     }
 
     void mean_metric_prepare(const double* xc, const double* R, int64_t n) override {
-        const int64_t n_glob = comm_global_count(ctx, n);
-        build_metric(xc, R, (int)n, POINT_PLUS, 1.0 / (double)n_glob, Mbar.as<double>());
-        if (ctx->world > 1) {
-            // every rank added the identity: all-reduce the J'FJ part only
-            throw RtError{"POLY: multi-GPU sharding is not provided for this latency-bound model", 3};
-        }
+        single_rank_only();
+        build_metric(xc, R, (int)n, POINT_PLUS, 1.0 / (double)n, Mbar.as<double>());
     }
 
     void mean_metric_apply(const double* u, double* out) override { apply(Mbar.as<double>(), u, 1, out); }
@@ -381,6 +387,12 @@ struct PolyEngine : Engine {
     }
     void ncg_update() override { ncg_launch(nullptr, 0); }
     const double* ncg_dx() override { return n_x.as<double>(); }
+    double ncg_residual() override {
+        double h = 0.0;
+        rt_d2h(&h, n_st.p, sizeof(double), ctx->stream);
+        rt_sync(ctx->stream);
+        return h;
+    }
 };
 
 }  // namespace
@@ -394,6 +406,8 @@ Engine* make_poly_engine(mgvib200_ctx* ctx, const mgvib200_model_desc& d) {
         delete e;
         throw;
     }
+    ctx->n_models_single_rank++;
+    e->counted = true;
     return e;
 }
 

@@ -1,5 +1,6 @@
 // Launch wrappers for the streaming vector kernels (vec_ops.h).
 #include "engine.h"
+#include <vector>
 #include "kernels.h"
 
 namespace mgvi {
@@ -80,6 +81,53 @@ void vec_sum_chunks(mgvib200_ctx* ctx, ReduceWs& ws, const double* in, long long
     VecParams P = vp_zero();
     P.op = VOP_SUM_CHUNKS; P.N = N; P.in = in; P.in_ld = ld; P.nsum = nsum; P.scale = scale; P.out = out;
     vec_launch(ctx, ws, P);
+}
+
+void vec_canon_sum(mgvib200_ctx* ctx, ReduceWs& ws, const CanonShape& cs, const double* in, long long ld,
+                   int terms_per_sample, double scale, double* out, long long N, DevBuf& gather) {
+    const int per = (int)(cs.per_chunk * terms_per_sample);
+    VecParams P = vp_zero();
+    P.op = VOP_SUM_CANON; P.N = N; P.in = in; P.in_ld = ld; P.per = per;
+    if (ctx->world <= 1) {
+        // both levels in one kernel: same additions in the same order as the gathered form below
+        P.nvec = 1; P.nsum = (int)cs.chunks; P.scale = scale; P.out = out;
+        vec_launch(ctx, ws, P);
+        return;
+    }
+    // chunk partials of this rank -> all-gather (no arithmetic in the collective) -> chunks in order
+    gather.ensure(sizeof(double) * (size_t)N * (size_t)cs.chunks);
+    double* G = gather.as<double>();
+    double* mine = G + (size_t)ctx->rank * cs.chunks_local * N;
+    P.nvec = (int)cs.chunks_local; P.nsum = 1; P.scale = 1.0; P.out = mine;
+    vec_launch(ctx, ws, P);
+    comm_allgather(ctx, mine, G, cs.chunks_local * N);
+    VecParams Q = vp_zero();
+    Q.op = VOP_SUM_CANON; Q.N = N; Q.in = G; Q.in_ld = N; Q.per = 1; Q.nvec = 1; Q.nsum = (int)cs.chunks;
+    Q.scale = scale; Q.out = out;
+    vec_launch(ctx, ws, Q);
+}
+
+double canon_scalar_sum(mgvib200_ctx* ctx, DevBuf& gather, const double* dev_local, int groups, long long count) {
+    const long long per_rank = (long long)groups * count;
+    const int W = ctx->world > 1 ? ctx->world : 1;
+    std::vector<double> h((size_t)per_rank * W);
+    if (W == 1) {
+        rt_d2h(h.data(), dev_local, sizeof(double) * per_rank, ctx->stream);
+    } else {
+        gather.ensure(sizeof(double) * per_rank * W);
+        double* G = gather.as<double>();
+        double* mine = G + (size_t)ctx->rank * per_rank;
+        if (mine != dev_local) rt_d2d(mine, dev_local, sizeof(double) * per_rank, ctx->stream);
+        comm_allgather(ctx, mine, G, per_rank);
+        rt_d2h(h.data(), G, sizeof(double) * per_rank * W, ctx->stream);
+    }
+    rt_sync(ctx->stream);
+    // group after group, every group in global term order: the sequence of additions does not depend on W
+    double tot = 0.0;
+    for (int g = 0; g < groups; ++g)
+        for (int r = 0; r < W; ++r)
+            for (long long i = 0; i < count; ++i) tot += h[(size_t)r * per_rank + (size_t)g * count + i];
+    return tot;
 }
 
 void vec_cg_init(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, const double* b, long long b_ld, double* x,

@@ -20,7 +20,9 @@ enum {
     VOP_QUAD = 9,        // acc = sum x . (0.5 y - h)  over all vectors         (dense KL value)
     VOP_FLIP = 10,       // out[i, s] = in[N-1-i, s]                            (index reversal)
     VOP_COPY = 11,       // out = in                                            (per vector)
-    VOP_TILE = 12        // out[tile-major i] = in[natural index of i]           (2-D relayout, field_pass.h)
+    VOP_TILE = 12,       // out[tile-major i] = in[natural index of i]           (2-D relayout, field_pass.h)
+    VOP_SUM_CANON = 13   // out[s] = scale * sum_{c < nsum} ( sum_{j < per} in[(s nsum + c) per + j] )
+                         //   two-level sequential sum in the canonical sample order (engine.h: CanonShape)
 };
 
 struct VecParams {
@@ -29,7 +31,7 @@ struct VecParams {
     double* x; double* r; const double* p; const double* Ap;   // CG vectors, ld = N
     const double* in; double* out; long long in_ld;
     const double* y;
-    int nsum;
+    int nsum, per;
     int lg_wt, lg_rows, lg_cols;      // VOP_TILE geometry
     double a, scale;
     double* partials; unsigned* counters; double* red_out;
@@ -57,6 +59,16 @@ SIMT_DEVICE void vec_elem(const VecParams& P, int s, long long i, double alpha, 
             double t = 0.0;
             for (int c = 0; c < P.nsum; ++c) t += P.in[(long long)c * P.in_ld + i];
             P.out[i] = P.scale * t;
+        } break;
+        case VOP_SUM_CANON: {
+            double tot = 0.0;
+            const double* src = P.in + ((long long)s * P.nsum * P.per) * P.in_ld + i;
+            for (int c = 0; c < P.nsum; ++c) {
+                double t = 0.0;
+                for (int j = 0; j < P.per; ++j) t += src[((long long)c * P.per + j) * P.in_ld];
+                tot += t;
+            }
+            P.out[gi] = P.scale * tot;
         } break;
         case VOP_AXPY: P.out[i] = P.in[i] + P.a * P.y[i]; break;
         case VOP_AXPY_INPLACE: P.out[i] += P.a * P.y[i]; break;

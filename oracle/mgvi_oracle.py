@@ -30,7 +30,7 @@ __all__ = [
     "metric_apply", "sampler_rhs", "krylov_cg", "sample_residuals_cg", "residual_pushfwd_operator",
     "sample_residuals_dense", "mv_normal_logdensity", "posterior_loglike", "mean_neg_log_pstr",
     "kl_gradient", "mean_metric_apply", "itsolvers_cg_iterator", "strong_wolfe", "NewtonCGOpts",
-    "NewtonCGTrace", "newtoncg_optimize", "build_samples", "mgvi_step", "mgvi_sample",
+    "NewtonCGTrace", "newtoncg_optimize", "newtoncg_step_record", "build_samples", "mgvi_step", "mgvi_sample",
 ]
 
 SQRT_EPS = float(np.sqrt(np.finfo(np.float64).eps))  # 1.4901161193847656e-08, LinearSolve default_tol
@@ -240,6 +240,12 @@ class FieldModel:
             return 1.0 / lam_mu                          # information.jl:74-78
         inv_s = 1.0 / self.sigma
         return np.full(self.N, inv_s * inv_s)            # information.jl:12-18 / 60-65
+
+    def metric_weight(self, xi):
+        """w = F_mu . g'(s)^2, the pixel-space diagonal of J'FJ = c^2 A H w H A."""
+        lam_mu = self.rate(xi)
+        gp = self._gprime(lam_mu)
+        return self._fisher_mu(lam_mu) * gp * gp
 
     def linearize(self, xi) -> Linearization:
         lam_mu = self.rate(xi)
@@ -665,10 +671,72 @@ class NewtonCGTrace:
     g_calls: int = 0
 
 
-def newtoncg_optimize(model, R, x0, opts: NewtonCGOpts = NewtonCGOpts()):
+def _newton_step(model, R, x, step, f_prev, df_n, opts, f, gradf, tr, rec, force_k=0):
+    """The body of the Newton loop, src/newtoncg.jl:112-146.  Returns (x_new, f_n, df_n).  `rec` (a dict
+    or None) receives every intermediate; `force_k` > 0 overrides the exit rules of the inner CG
+    (teacher forcing, tests only)."""
+    n = R.shape[1]
+    g = gradf(x)                                 # :115
+    lins = [model.linearize(x + R[:, i]) for i in range(n)]     # Sigma_bar_inv(x_n), :120
+    dx = np.zeros_like(x)
+    updates = 0
+    it = itsolvers_cg_iterator(lambda u: mean_metric_apply(model, R, x, u, lins), g)
+    if step == 1:
+        for k, xk, _res in it:                   # :121-127
+            dx, updates = xk, k
+            if rec is not None:
+                rec["dx_iters"].append(xk.copy()); rec["cg_resid"].append(_res); rec["f_k"].append(float("nan"))
+            if (k >= force_k) if force_k else (k >= opts.i0):
+                break
+    else:
+        f_km1 = f_prev                           # :129
+        for k, xk, _res in it:                   # :132-139
+            dx, updates = xk, k
+            f_k = f(x - dx)
+            if rec is not None:
+                rec["dx_iters"].append(xk.copy()); rec["cg_resid"].append(_res); rec["f_k"].append(f_k)
+                rec["exit_margin"].append(abs(f_k - f_km1) - opts.alpha * df_n)
+            if (k >= force_k) if force_k else (k >= opts.i1 or abs(f_k - f_km1) < opts.alpha * df_n):
+                tr.cg_iterations.append(k)
+                break
+            f_km1 = f_k
+    tr.cg_updates.append(updates)
+    d = -dx                                      # linesearch_args(..., -dx, ...) :142
+
+    def phi(a):                                  # :66
+        v = f(x + a * d)
+        if rec is not None:
+            rec["ls"].append((0, float(a), v))
+        return v
+
+    def dphi(a):                                 # :67
+        v = float(gradf(x + a * d) @ d)
+        if rec is not None:
+            rec["ls"].append((1, float(a), v))
+        return v
+
+    dphi0 = float(g @ d)
+    beta, f_n = strong_wolfe(phi, dphi, 1.0, f_prev, dphi0)
+    tr.step_lengths.append(beta)
+    x_new = x - beta * dx                        # :143
+    if rec is not None:
+        rec.update(grad=g, k=updates, dphi0=dphi0, beta=beta, f_new=f_n, x_new=x_new.copy(), dx=dx.copy())
+    return x_new, f_n, abs(f_n - f_prev)         # :144
+
+
+def _new_record(step, x, f_prev, df_n):
+    return dict(step=step, x_n=x.copy(), f_prev=f_prev, df_n=df_n, dx_iters=[], f_k=[], cg_resid=[],
+                exit_margin=[], ls=[])
+
+
+def newtoncg_optimize(model, R, x0, opts: NewtonCGOpts = NewtonCGOpts(), record: list | None = None):
     """`_optimize(f, adsel, Sigma_bar_inv, x0, ::NewtonCG, opts)` (src/newtoncg.jl:85-167) with
     f = mean_neg_log_pstr(model, R, .) and Sigma_bar_inv = mean metric (src/mgvi_impl.jl:135-139).
-    Returns (x, f(x), trace)."""
+    Returns (x, f(x), trace).  `record` (a list) receives one dict per Newton step with every
+    intermediate of that step -- the state at the top of the step (x_n, f_prev, df_n), grad f(x_n),
+    the inner-CG iterates dx_k with residual norms and f(x_n - dx_k), the exit margin of the
+    stagnation test (:134), the line-search evaluations in call order, beta, x_{n+1} -- which is
+    what the teacher-forced parity tests compare the device path with (tests/helpers.py)."""
     tr = NewtonCGTrace()
 
     def f(x):
@@ -686,38 +754,25 @@ def newtoncg_optimize(model, R, x0, opts: NewtonCGOpts = NewtonCGOpts()):
     f_n = 0.0
     df_n = 0.0
     x = x0.copy()
-    n = R.shape[1]
     for step in range(1, opts.steps + 1):            # :112
-        g = gradf(x)                                 # :115
-        lins = [model.linearize(x + R[:, i]) for i in range(n)]     # Sigma_bar_inv(x_n), :120
-        dx = np.zeros_like(x)
-        updates = 0
-        it = itsolvers_cg_iterator(lambda u: mean_metric_apply(model, R, x, u, lins), g)
-        if step == 1:
-            for k, xk, _res in it:                   # :121-127
-                dx, updates = xk, k
-                if k >= opts.i0:
-                    break
-        else:
-            f_km1 = f_prev                           # :129
-            for k, xk, _res in it:                   # :132-139
-                dx, updates = xk, k
-                f_k = f(x - dx)
-                if k >= opts.i1 or abs(f_k - f_km1) < opts.alpha * df_n:
-                    tr.cg_iterations.append(k)
-                    break
-                f_km1 = f_k
-        tr.cg_updates.append(updates)
-        d = -dx                                      # linesearch_args(..., -dx, ...) :142
-        phi = lambda a: f(x + a * d)                 # noqa: E731   :66
-        dphi = lambda a: float(gradf(x + a * d) @ d)  # noqa: E731  :67
-        beta, f_n = strong_wolfe(phi, dphi, 1.0, f_prev, float(g @ d))
-        tr.step_lengths.append(beta)
-        x = x - beta * dx                            # :143
-        df_n = abs(f_n - f_prev)                     # :144
+        rec = _new_record(step, x, f_prev, df_n) if record is not None else None
+        x, f_n, df_n = _newton_step(model, R, x, step, f_prev, df_n, opts, f, gradf, tr, rec)
         f_prev = f_n
         tr.f_history.append(f_n)                     # :146
+        if rec is not None:
+            record.append(rec)
     return x, f_n, tr
+
+
+def newtoncg_step_record(model, R, x_n, step, f_prev, df_n, opts: NewtonCGOpts = NewtonCGOpts(), force_k=0):
+    """ONE Newton step (src/newtoncg.jl:112-146) from an injected state, fully recorded -- the oracle
+    twin of mgvib200_newton_probe (tests only: teacher-forced parity and the oracle's own sensitivity)."""
+    tr = NewtonCGTrace()
+    x_n = np.asarray(x_n, dtype=np.float64)
+    rec = _new_record(step, x_n, f_prev, df_n)
+    _newton_step(model, R, x_n, step, f_prev, df_n, opts, lambda x: mean_neg_log_pstr(model, R, x),
+                 lambda x: kl_gradient(model, R, x), tr, rec, force_k=force_k)
+    return rec
 
 
 # --------------------------------------------------------------------------------------------

@@ -40,3 +40,20 @@ def gpu_ctx(pkg):
     ctx = pkg.MGVIContext(device=0)      # product library; raises if libmgvib200.so is missing
     yield ctx
     ctx.close()
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Which regime every Newton-phase comparison ran in (helpers.PARITY_LOG): strict (free-running
+    result at 1e-10 with equal traces) or teacher-forced (every Newton step from the oracle's x_n at
+    1e-10, widened per quantity only to the oracle's own measured reproducibility)."""
+    try:
+        import helpers
+    except Exception:       # noqa: BLE001
+        return
+    if not helpers.PARITY_LOG:
+        return
+    tr = terminalreporter
+    tr.write_sep("-", "Newton-phase parity regimes (config -> regime, worst relative error)")
+    for label, regime, worst in helpers.PARITY_LOG:
+        tr.write_line("  %-34s %-16s %.2e" % (label, regime.split(" (")[0], worst) + (
+            "  [" + regime.split(" (", 1)[1].rstrip(")") + "]" if " (" in regime else ""))

@@ -63,54 +63,169 @@ def check_field_ops(pkg, ctx, cfg, nprobe=3, check_step=True):
         res, cn = pkg.mgvi_step(m, cfg["data"], n, c, pkg.MGVIConfig(linsolver=pkg.B200CG(**TIGHT)), ctx,
                                 draws=(cfg["Z1"], cfg["Z2"]))
         ref = O.mgvi_step(om, c, Z1=cfg["Z1"], Z2=cfg["Z2"], **TIGHT_O)
-        tr, otr = res.info["optimizer_output"], ref["trace"]
-        out["center"] = rel(cn, ref["center"])
-        out["samples"] = rel(res.samples, ref["samples"])
-        out["mnlp"] = abs(res.mnlp - ref["mnlp"]) / abs(ref["mnlp"])
-        out["trace_equal"] = (tr["cg_updates"] == otr.cg_updates and tr["f_calls"] == otr.f_calls and
-                              tr["g_calls"] == otr.g_calls and tr["cg_iterations"] == otr.cg_iterations)
-        out["steps"] = rel(tr["step_lengths"], otr.step_lengths)
-        # pairing: columns 2i and 2i+1 are symmetric about the updated centre
-        out["pairing"] = float(np.abs(res.samples[:, 0::2] + res.samples[:, 1::2] - 2 * cn[:, None]).max())
+        out["step_regime"] = assert_step_parity(pkg, m, om, cfg, res, cn, ref,
+                                                label="%s %s" % (cfg["kind"], "x".join(map(str, cfg.get("dims", ())))))
     m.close()
     return out
 
 
-def oracle_step_sensitivity(cfg, seed=0, **step_kw):
-    """How far the ORACLE's own mgvi_step moves when its inputs are perturbed at the rounding
-    level (data and centre scaled by 1 + 1e-15 * randn).  Newton-CG is a truncated iteration with
-    data-dependent exits and a cubic-interpolating line search (hard parts):
-    on ill-conditioned fixtures rounding noise is amplified far above 1e-10, and no implementation
-    can agree with the reference better than the reference agrees with itself.  Returns
-    (relative change of the updated centre, traces equal?)."""
-    om = oracle_model(cfg)
-    if not step_kw:
-        step_kw = dict(Z1=cfg["Z1"], Z2=cfg["Z2"], **TIGHT_O)
-    base = O.mgvi_step(om, cfg["center"], **step_kw)
-    rng = np.random.default_rng(seed)
-    cfg2 = dict(cfg)
-    cfg2["data"] = cfg["data"] * (1.0 + 1e-15 * rng.standard_normal(cfg["data"].shape))
-    c2 = cfg["center"] * (1.0 + 1e-15 * rng.standard_normal(cfg["center"].shape))
-    pert = O.mgvi_step(oracle_model(cfg2), c2, **step_kw)
-    same = (base["trace"].cg_updates == pert["trace"].cg_updates and base["trace"].f_calls == pert["trace"].f_calls)
-    return rel(pert["center"], base["center"]), same
+# ------------------------------------------------------------------------------------------------
+# Newton phase (rows a12 / a14): teacher-forced, per-step parity.
+#
+# MGVI's NewtonCG (src/newtoncg.jl:85-167) is a TRUNCATED iteration with data-dependent exits (the
+# KL-stagnation test :134, the strong-Wolfe bracket/zoom branches :142).  On ill-conditioned
+# fixtures a 1e-15 perturbation of the inputs moves the ORACLE's own end-to-end result by up to
+# O(1) (measured: 2e-2 at 64 x 64, 0.89 at 256 x 256), so comparing only the final centre says
+# nothing there.  Instead every Newton step is compared on its own: the oracle's state at the top
+# of step n (x_n, f_prev, df_n) is injected into the device path (mgvib200_newton_probe) and that
+# step's gradient, mean metric weight, every inner-CG iterate dx_k with its residual norm, every
+# f(x_n - dx_k), every line-search evaluation, the accepted step and x_{n+1} are compared.  No code
+# path returns without numeric assertions.
+# ------------------------------------------------------------------------------------------------
+PARITY_LOG = []      # (label, regime, worst relative error) per checked configuration; printed by conftest
 
 
-def assert_step_parity(cfg, center_err, samples_err, trace_equal, **step_kw):
-    """north_star tolerance (1e-10) on the updated mean, widened only where the oracle itself is
-    measurably less reproducible than that."""
-    if center_err < RTOL and samples_err < RTOL and trace_equal:
-        return
-    sens, same = max((oracle_step_sensitivity(cfg, seed, **step_kw) for seed in range(3)), key=lambda t: t[0])
-    assert sens > 1e-12, ("oracle is well conditioned here, yet parity failed", center_err, samples_err, sens)
-    if sens > 1e-6 or not same:
-        # chaotic regime: the oracle's own branch trace / result flips under 1e-15 perturbations, so
-        # the updated mean carries no comparable digits; callers still compare the residuals
-        # (antithetic half-differences) and every well-conditioned row tightly.
-        return "chaotic"
-    tol = max(RTOL, 100.0 * sens)
-    assert center_err < tol and samples_err < tol, (center_err, samples_err, sens)
-    return "widened"
+def oracle_wbar(om, x, R):
+    """mean_i w_i at the '+' points x + r_i (src/mgvi_impl.jl:137-138; field models)."""
+    return np.mean([om.metric_weight(x + R[:, i]) for i in range(R.shape[1])], axis=0)
+
+
+def _scal_err(a, b, scale):
+    return abs(a - b) / max(abs(scale), 1e-300)
+
+
+def _step_errors(got, rec, om, R, check_wbar, k):
+    """Per-quantity relative errors of one recorded Newton step (`got`: the device probe or a perturbed
+    oracle run, as a dict with the probe's keys) against the oracle record `rec`."""
+    e = {}
+    e["grad"] = rel(got["grad"], rec["grad"])
+    if check_wbar and got.get("wbar") is not None:
+        e["wbar"] = rel(got["wbar"], oracle_wbar(om, rec["x_n"], R))
+    gnorm = np.linalg.norm(rec["grad"])
+    if k:
+        dxo = np.stack(rec["dx_iters"], axis=1)
+        e["dx_k"] = max(rel(got["dx_iters"][:, j], dxo[:, j]) for j in range(k))
+        # residual norms fall by many orders of magnitude: compare on the scale of ||g||
+        e["cg_resid"] = max(_scal_err(got["cg_resid"][j], rec["cg_resid"][j], gnorm) for j in range(k))
+        if rec["step"] > 1:
+            e["f_k"] = max(_scal_err(got["f_k"][j], rec["f_k"][j], rec["f_k"][j]) for j in range(k))
+    dnorm = np.linalg.norm(rec["dx"])
+    e["dphi0"] = _scal_err(got["dphi0"], rec["dphi0"], gnorm * dnorm)
+    # line search: the common prefix of the two evaluation sequences (same kinds) -- abscissae and values
+    npre = 0
+    for (k1, _, _), (k2, _, _) in zip(got["ls"], rec["ls"]):
+        if k1 != k2:
+            break
+        npre += 1
+    pairs = list(zip(got["ls"][:npre], rec["ls"][:npre]))
+    e["ls_a"] = max([_scal_err(a1, a2, a2) for (_, a1, _), (_, a2, _) in pairs] or [0.0])
+    e["ls_phi"] = max([_scal_err(v1, v2, v2) for (kd, _, v1), (_, _, v2) in pairs if kd == 0] or [0.0])
+    # phi'(a) = grad f(x + a d) . d  -- compared on the scale ||grad|| ||d|| (it passes through zero)
+    e["ls_dphi"] = max([_scal_err(v1, v2, gnorm * dnorm) for (kd, _, v1), (_, _, v2) in pairs if kd == 1] or [0.0])
+    same_ls = npre == len(got["ls"]) == len(rec["ls"])
+    if same_ls:
+        e["beta"] = _scal_err(got["beta"], rec["beta"], rec["beta"])
+        e["f_new"] = _scal_err(got["f_new"], rec["f_new"], rec["f_new"])
+        e["x_new"] = rel(got["x_new"], rec["x_new"])
+    return e, same_ls
+
+
+def _oracle_step_sensitivity(om, R, rec, opts, nseeds=2):
+    """The ORACLE's own reproducibility of one Newton step: the same step from x_n and R perturbed at
+    the rounding level (x (1 + 1e-16 randn)), per quantity.  The k-th iterate of a TRUNCATED CG amplifies
+    rounding like cond^(k/2) (measured against 50-digit arithmetic in tests/test_oracle_pinning.py: the
+    reference's 40-pixel fixture loses 6 digits in 5 updates at a condition number of 6e3, and iterates
+    beyond k ~ 25 of a 32 x 32 field move by > 1e-9 under a 1e-16 perturbation); no implementation can
+    agree with the reference better than the reference agrees with itself, so this is what the tolerance
+    is widened to -- per quantity, measured, and reported."""
+    sens, ls_stable = {}, True
+    k = rec["k"]
+    for seed in range(nseeds):
+        rng = np.random.default_rng(1000 + seed)
+        xp = rec["x_n"] * (1.0 + 1e-16 * rng.standard_normal(rec["x_n"].shape))
+        Rp = R * (1.0 + 1e-16 * rng.standard_normal(R.shape))
+        pert = O.newtoncg_step_record(om, Rp, xp, rec["step"], rec["f_prev"], rec["df_n"], opts, force_k=k)
+        got = dict(pert)
+        got["dx_iters"] = np.stack(pert["dx_iters"], axis=1) if pert["dx_iters"] else np.zeros((xp.size, 0))
+        got["wbar"] = None
+        e, same = _step_errors(got, rec, om, Rp, False, min(k, len(pert["dx_iters"])))
+        ls_stable = ls_stable and same
+        for key, v in e.items():
+            sens[key] = max(sens.get(key, 0.0), float(v))
+    return sens, ls_stable
+
+
+def assert_newton_teacher_forced(pkg, model, om, R, x0, opts_kw=None, label="", tol=RTOL, check_wbar=True):
+    """Runs the oracle's NewtonCG with recording, then replays EVERY Newton step on the device from
+    the oracle's x_n (mgvib200_newton_probe, inner-CG update count forced to the oracle's).  Asserts,
+    per step, at `tol` (relative 1e-10): grad f(x_n), w_bar, dx_k (every CG update), CG residual norms,
+    f_k, phi'(0), every line-search (a, phi / phi') pair in call order, beta, f_{n+1}, x_{n+1}; and that
+    the device's own exit rule fires at the oracle's k wherever the oracle's margin at the decision is
+    not itself at rounding level.  A quantity that misses 1e-10 is re-judged against 100 x the oracle's
+    own measured sensitivity for that quantity (`_oracle_step_sensitivity`); the regime is logged.
+    Returns the per-step error table."""
+    opts_kw = opts_kw or {}
+    oopts = O.NewtonCGOpts(**opts_kw)
+    recs = []
+    O.newtoncg_optimize(om, R, x0, oopts, record=recs)
+    table, widened = [], []
+    for rec in recs:
+        k = rec["k"]
+        pr = pkg.newton_probe(model, R, rec["x_n"], rec["step"], rec["f_prev"], rec["df_n"], force_k=k,
+                              max_rec=max(k, 1), optimizer=pkg.NewtonCG(**opts_kw), want_wbar=check_wbar)
+        assert pr["k_done"] == k, (label, rec["step"], pr["k_done"], k)
+        e, same_ls = _step_errors(pr, rec, om, R, check_wbar, k)
+        # the step's own exit rule
+        if k and rec["step"] > 1:
+            # the stagnation test |f_k - f_{k-1}| < alpha df_n compares differences of f: the oracle's own
+            # decision is only meaningful where its margin exceeds the rounding of f
+            noise = 64 * np.finfo(float).eps * abs(rec["f_prev"])
+            if not any(abs(mg) <= noise for mg in rec["exit_margin"]):
+                assert pr["k_own_exit"] == k, (label, rec["step"], pr["k_own_exit"], k)
+        elif k:
+            i0 = opts_kw.get("i0", 5)
+            assert pr["k_own_exit"] == (i0 if k >= i0 else 0), (label, pr["k_own_exit"], k)
+        bad = [key for key, v in e.items() if not v < tol]
+        if bad or not same_ls:
+            sens, ls_stable = _oracle_step_sensitivity(om, R, rec, oopts)
+            assert same_ls or not ls_stable, (label, "step", rec["step"], "line-search branch sequence differs while "
+                                              "the oracle's own is stable", pr["ls"], rec["ls"])
+            for key in bad:
+                lim = max(tol, 100.0 * sens.get(key, 0.0))
+                assert e[key] < lim, (label, "step", rec["step"], key, e[key], "oracle self-sensitivity", sens.get(key), e)
+                widened.append("%s@%d: %.1e (oracle self %.1e)" % (key, rec["step"], e[key], sens.get(key, 0.0)))
+        table.append(dict(step=rec["step"], k=k, **e))
+    worst = max(max(v for kk, v in t.items() if kk not in ("step", "k")) for t in table) if table else 0.0
+    PARITY_LOG.append((label, "teacher-forced" + (" (widened to the oracle's own reproducibility: %s)" % "; ".join(widened)
+                                                  if widened else ""), worst))
+    return table
+
+
+def assert_step_parity(pkg, model, om, cfg, res, center, ref, *, label="", opts_kw=None):
+    """End-to-end mgvi_step against the oracle's.  The residual samples (which do not pass through the
+    optimiser) and the KL value at the device's own result are ALWAYS asserted at 1e-10.  The
+    free-running updated mean is asserted at 1e-10 with full trace equality where it agrees
+    ("strict"); where it does not, the Newton phase is replayed teacher-forced (every step's
+    quantities at 1e-10 from the oracle's x_n) -- there is no path without numeric assertions."""
+    tr, otr = res.info["optimizer_output"], ref["trace"]
+    Rdev = 0.5 * (res.samples[:, 0::2] - res.samples[:, 1::2])
+    Rref = ref["residuals"]
+    assert rel(Rdev, Rref) < RTOL, (label, "residuals", rel(Rdev, Rref))
+    assert np.abs(res.samples[:, 0::2] + res.samples[:, 1::2] - 2 * center[:, None]).max() < 1e-12
+    # the returned mnlp IS the KL estimate at the returned centre (oracle evaluation at the device's result)
+    f_at = O.mean_neg_log_pstr(om, Rdev, center)
+    assert abs(f_at - res.mnlp) <= RTOL * abs(f_at), (label, "mnlp", f_at, res.mnlp)
+    assert tr["f_history"][-1] <= tr["f_history"][0] + 1e-9 * abs(tr["f_history"][0]), (label, tr["f_history"])
+    # first Newton-phase quantities are free of accumulated drift: f(x_0) at 1e-10
+    assert abs(tr["f_history"][0] - otr.f_history[0]) <= RTOL * abs(otr.f_history[0]), (label, "f0")
+    ec, es = rel(center, ref["center"]), rel(res.samples, ref["samples"])
+    trace_equal = (tr["cg_updates"] == otr.cg_updates and tr["f_calls"] == otr.f_calls and
+                   tr["g_calls"] == otr.g_calls and tr["cg_iterations"] == otr.cg_iterations)
+    if ec < RTOL and es < RTOL and trace_equal:
+        PARITY_LOG.append((label, "strict", max(ec, es)))
+        return "strict"
+    assert_newton_teacher_forced(pkg, model, om, Rref, cfg["center"], opts_kw, label=label)
+    return "teacher-forced"
 
 
 def assert_field_ops(out, cfg=None):
@@ -120,15 +235,8 @@ def assert_field_ops(out, cfg=None):
     a, b = out["iters"]
     # at reltol 1e-12 the tail of the solve sits on the rounding floor: counts may differ by a few
     assert all(abs(x - y) <= 3 + 0.10 * y for x, y in zip(a, b)), out["iters"]
-    if "center" in out:
-        if cfg is None:
-            for k in ("center", "samples", "mnlp"):
-                assert out[k] < RTOL, (k, out)
-            assert out["trace_equal"], out
-            assert out["steps"] < 1e-8, out
-        else:
-            assert_step_parity(cfg, out["center"], out["samples"], out["trace_equal"])
-        assert out["pairing"] < 1e-12, out
+    if "step_regime" in out:
+        assert out["step_regime"] in ("strict", "teacher-forced"), out
 
 
 def check_poly_ops(pkg, ctx, cfg):
@@ -174,11 +282,8 @@ def check_poly_ops(pkg, ctx, cfg):
         res, cn = pkg.mgvi_step(m, cfg["data"], n, c, cfgm, ctx, draws=draws)
         ref = O.mgvi_step(om, c, Z1=cfg["Z1"], Z2=cfg["Z2"], Z=cfg["Z"], dense=dense, atol=0.0, rtol=1e-12,
                           itmax=50) if not dense else O.mgvi_step(om, c, Z=cfg["Z"], dense=True)
-        tr, otr = res.info["optimizer_output"], ref["trace"]
         key = "dense_step" if dense else "cg_step"
-        kw = dict(Z=cfg["Z"], dense=True) if dense else dict(Z1=cfg["Z1"], Z2=cfg["Z2"], atol=0.0, rtol=1e-12, itmax=50)
-        assert_step_parity(cfg, rel(cn, ref["center"]), rel(res.samples, ref["samples"]),
-                           tr["cg_updates"] == otr.cg_updates and tr["f_calls"] == otr.f_calls, **kw)
+        out[key + "_regime"] = assert_step_parity(pkg, m, om, cfg, res, cn, ref, label="poly %s" % key)
         # the residuals (antithetic half-differences) do not pass through the optimiser
         out[key] = rel(res.samples[:, 0::2] - res.samples[:, 1::2], ref["samples"][:, 0::2] - ref["samples"][:, 1::2])
     m.close()
@@ -217,9 +322,7 @@ def check_dense_ops(pkg, ctx, cfg, with_step=True):
     if with_step:
         res, cn = pkg.mgvi_step(m, cfg["data"], n, c, pkg.MGVIConfig(linsolver=pkg.MatrixInversion()), ctx, draws=cfg["Z"])
         ref = O.mgvi_step(om, c, Z=cfg["Z"], dense=True)
-        tr, otr = res.info["optimizer_output"], ref["trace"]
-        assert_step_parity(cfg, rel(cn, ref["center"]), rel(res.samples, ref["samples"]),
-                           tr["cg_updates"] == otr.cg_updates and tr["f_calls"] == otr.f_calls, Z=cfg["Z"], dense=True)
+        out["dense_step_regime"] = assert_step_parity(pkg, m, om, cfg, res, cn, ref, label="dense %dx%d" % cfg["J"].shape)
         out["dense_step_residuals"] = rel(res.samples[:, 0::2] - res.samples[:, 1::2],
                                           ref["samples"][:, 0::2] - ref["samples"][:, 1::2])
     m.close()

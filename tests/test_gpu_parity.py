@@ -10,7 +10,7 @@ import pytest
 
 import oracle as O
 from golden_io import load_golden
-from helpers import RTOL, TIGHT, assert_field_ops, assert_step_parity, check_field_ops, oracle_model, rel
+from helpers import RTOL, TIGHT, assert_field_ops, check_field_ops, oracle_model, rel
 
 pytestmark = pytest.mark.gpu
 
@@ -80,11 +80,16 @@ def test_golden_vectors(pkg, gpu_ctx, name):
     assert abs(f - gold["f"]) / abs(gold["f"]) < RTOL and rel(g, gold["grad"]) < RTOL
     res, c = pkg.mgvi_step(m, cfg["data"], cfg["n_residuals"], cfg["center"],
                            pkg.MGVIConfig(linsolver=pkg.B200CG(**TIGHT)), gpu_ctx, draws=(cfg["Z1"], cfg["Z2"]))
-    tr = res.info["optimizer_output"]
-    trace_equal = (tr["cg_updates"] == gold["tr_cg_updates"].tolist() and tr["f_calls"] == int(gold["tr_f_calls"]))
-    assert_step_parity(cfg, rel(c, gold["step_center"]), rel(res.samples, gold["step_samples"]), trace_equal)
+    # residuals (antithetic half-differences) do not pass through the optimiser: tight against the fixture
     assert rel(res.samples[:, 0::2] - res.samples[:, 1::2],
                gold["step_samples"][:, 0::2] - gold["step_samples"][:, 1::2]) < RTOL
+    assert abs(res.info["optimizer_output"]["f_history"][0] - gold["tr_f_history"][0]) <= RTOL * abs(gold["tr_f_history"][0])
+    # Newton phase: strict end-to-end where the oracle's trajectory is reproduced, otherwise every Newton
+    # step teacher-forced from the oracle's x_n (helpers.assert_step_parity)
+    from helpers import TIGHT_O, assert_step_parity
+    om = oracle_model(cfg)
+    ref = O.mgvi_step(om, cfg["center"], Z1=cfg["Z1"], Z2=cfg["Z2"], **TIGHT_O)
+    assert_step_parity(pkg, m, om, cfg, res, c, ref, label="golden " + name)
     m.close()
 
 
