@@ -311,19 +311,23 @@ def main():
     barrier()
     clocks = ClockSampler(local_rank)
     ctx.launch_count(reset=True)
-    lib.profile_begin(ctx.handle)
     t0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(K):
         dev_ms += step_dev()
     barrier()
     wall_s = time.perf_counter() - t0
+    launches = ctx.launch_count()
+    clk = clocks.stop()
+    # per-kernel breakdown: a separate, untimed pass with CUDA events around every launch (the timed steps
+    # above replay CUDA graphs; events between graph nodes would serialise them)
+    lib.profile_begin(ctx.handle)
+    for _ in range(min(K, 2)):
+        step_dev()
     tags = (C.c_int32 * 64)()
     tms = (C.c_double * 64)()
     tcnt = (C.c_int64 * 64)()
     ntag = lib.profile_end(ctx.handle, 64, tags, tms, tcnt)
-    launches = ctx.launch_count()
-    clk = clocks.stop()
     tt = torch.tensor([dev_ms, wall_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -212,6 +212,16 @@ typedef struct {
 int mgvib200_newton_probe(mgvib200_model* m, const double* x_n, const double* R, int64_t n,
                           const mgvib200_newtoncg_opts* opts, mgvib200_probe_rec* probe);
 
+/* Parity probe of single updates of the Newton inner CG (IterativeSolvers cg_iterator!, call site
+ * src/newtoncg.jl:120-139) on Sigma_bar_inv(x_n): for each of n_states injected iterator states
+ * (x, r, u, residual, prev_residual -- as they stand BEFORE an update; columns of X, Rr, U) performs
+ * exactly that update through the device CG kernels and returns the new iterate and residual norm.
+ * The k-th iterate of a truncated CG amplifies rounding like cond^(k/2), so iterates are compared one
+ * update at a time from the reference state.  FIELD_DHT models. */
+int mgvib200_ncg_probe(mgvib200_model* m, const double* x_n, const double* R, int64_t n, int64_t n_states,
+                       const double* X, const double* Rr, const double* U, const double* res, const double* prev,
+                       double* X_out /* n_theta x n_states */, double* res_out /* n_states */);
+
 /* a13  _build_samples  src/mgvi_impl.jl:152-156 : columns [c + r1, c - r1, c + r2, c - r2, ...] */
 int mgvib200_build_samples(mgvib200_model* m, const double* center, const double* R, int64_t n,
                            double* samples /* n_theta x 2n */);

@@ -753,6 +753,25 @@ def newton_probe(forward_model: _Model, R, x_n, step: int, f_prev: float, df_n: 
                 ls=[(int(pr.ls_kind[i]), float(pr.ls_a[i]), float(pr.ls_val[i])) for i in range(nls)])
 
 
+def ncg_probe(forward_model: _Model, R, x_n, states):
+    """Single updates of the Newton inner CG from injected iterator states (mgvib200_ncg_probe).
+    `states`: list of (x, r, u, residual, prev_residual) before an update -> (X_out (n_theta x k), residuals)."""
+    m, ctx = forward_model, forward_model.context
+    x_n = as_f64(x_n, (m.n_theta,))
+    R = np.asfortranarray(as_f64(R).reshape(m.n_theta, -1, order="F"))
+    k = len(states)
+    X = np.asfortranarray(np.stack([s[0] for s in states], axis=1)) if k else np.zeros((m.n_theta, 0), order="F")
+    Rr = np.asfortranarray(np.stack([s[1] for s in states], axis=1)) if k else X
+    U = np.asfortranarray(np.stack([s[2] for s in states], axis=1)) if k else X
+    res = np.array([s[3] for s in states], dtype=np.float64)
+    prev = np.array([s[4] for s in states], dtype=np.float64)
+    Xo = np.empty((m.n_theta, k), order="F")
+    ro = np.empty(k)
+    ctx.check(ctx.lib.ncg_probe(m.handle, ptr(x_n), ptr(R), R.shape[1], k, ptr(X), ptr(Rr), ptr(U), ptr(res), ptr(prev),
+                                ptr(Xo), ptr(ro)))
+    return Xo, ro
+
+
 def build_samples(forward_model: _Model, R, center):
     """`_build_samples` (src/mgvi_impl.jl:152-156)."""
     m, ctx = forward_model, forward_model.context

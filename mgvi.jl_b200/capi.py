@@ -103,6 +103,8 @@ EXPORTS = {
     "mgvib200_objective_eval": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
     "mgvib200_newton_probe": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, C.POINTER(NewtonCGOpts),
                                         C.POINTER(NewtonProbe)]),
+    "mgvib200_ncg_probe": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, C.c_int64, c_double_p, c_double_p,
+                                     c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "mgvib200_build_samples": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, c_double_p]),
     "mgvib200_step": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int,
                                 C.POINTER(CGOpts), C.POINTER(NewtonCGOpts), c_double_p, c_double_p, c_double_p,

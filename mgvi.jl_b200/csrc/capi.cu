@@ -306,6 +306,8 @@ int mgvib200_init(int device_id, mgvib200_ctx** out) {
         ctx->stream = rt_stream_create();
         ctx->ev0 = rt_event_create();
         ctx->ev1 = rt_event_create();
+        ctx->ev_poll[0] = rt_event_create();
+        ctx->ev_poll[1] = rt_event_create();
         ctx->h_pinned = (int*)rt_host_alloc(65536);
 #if defined(__CUDACC__) && !defined(MGVI_SIMT_EMU)
         cudaDeviceProp prop;
@@ -331,6 +333,8 @@ void mgvib200_destroy(mgvib200_ctx* ctx) {
     rt_host_free(ctx->h_pinned);
     rt_event_destroy(ctx->ev0);
     rt_event_destroy(ctx->ev1);
+    rt_event_destroy(ctx->ev_poll[0]);
+    rt_event_destroy(ctx->ev_poll[1]);
     rt_stream_destroy(ctx->stream);
     delete ctx;
 }
@@ -599,6 +603,30 @@ int mgvib200_newton_probe(mgvib200_model* m, const double* x_n, const double* R,
         probe->n_ls = 0;
         double f_prev = probe->f_prev, df_n = probe->df_n, f_n = 0.0;
         newton_one_step(m, x, rd, n, ncg_defaults(opts), probe->step, f_prev, df_n, f_n, tr, probe);
+        rt_sync(m->ctx->stream);
+    });
+}
+
+int mgvib200_ncg_probe(mgvib200_model* m, const double* x_n, const double* R, int64_t n, int64_t n_states,
+                       const double* X, const double* Rr, const double* U, const double* res, const double* prev,
+                       double* X_out, double* res_out) {
+    if (!m || !x_n || !R || !X || !Rr || !U || !res || !prev || !X_out || !res_out) return MGVIB200_ERR_INVALID;
+    return guarded(m->ctx, [&] {
+        need(n >= 1 && n_states >= 0, "ncg_probe: n must be >= 1, n_states >= 0");
+        rt_set_device(m->ctx->device);
+        const size_t nt = (size_t)m->eng->n_theta;
+        double* xd = stage_in(m, 0, x_n, nt);
+        double* rd = stage_in(m, 3, R, nt * n);
+        m->eng->mean_metric_prepare(xd, rd, n);                 // Sigma_bar_inv(x_n), src/newtoncg.jl:120
+        for (int64_t j = 0; j < n_states; ++j) {
+            double* a = stage_in(m, 1, X + j * nt, nt);
+            double* b = stage_in(m, 2, Rr + j * nt, nt);
+            double* c = stage_in(m, 5, U + j * nt, nt);
+            m->eng->ncg_set_state(a, b, c, res[j], prev[j]);
+            m->eng->ncg_update();
+            rt_d2h(X_out + j * nt, m->eng->ncg_dx(), sizeof(double) * nt, m->ctx->stream);
+            res_out[j] = m->eng->ncg_residual();
+        }
         rt_sync(m->ctx->stream);
     });
 }

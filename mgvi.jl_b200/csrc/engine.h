@@ -44,7 +44,7 @@ struct mgvib200_ctx {
     int64_t launches = 0;
     mgvi::Comm* comm = nullptr;
     int rank = 0, world = 1;
-    mgvi::rt_event ev0{}, ev1{};
+    mgvi::rt_event ev0{}, ev1{}, ev_poll[2]{};
     double sampler_ms = 0.0, newton_ms = 0.0;
     int64_t lockstep_iters = 0;
     int* h_pinned = nullptr;        // small pinned staging area (64 KB)
@@ -123,6 +123,11 @@ struct Engine {
     virtual const double* ncg_dx() = 0;     // current dx (device)
     // parity probe (mgvib200_newton_probe): residual norm of the inner CG, mean metric weight (host copy)
     virtual double ncg_residual() { return NAN; }
+    // inject the state of the IterativeSolvers iterator (x, r, u, residual, prev_residual) as it stands before
+    // an update (mgvib200_ncg_probe); the next ncg_update() performs exactly that update
+    virtual void ncg_set_state(const double*, const double*, const double*, double, double) {
+        throw RtError{"the Newton-CG state probe is provided for FIELD_DHT models", 3};
+    }
     virtual void get_mean_weights(double*) { throw RtError{"the mean metric weight is only exposed by FIELD_DHT models", 3}; }
 };
 

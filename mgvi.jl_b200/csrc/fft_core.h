@@ -146,10 +146,11 @@ SIMT_DEVICE void fft_line_forward(double2 (&v)[8], const LineView& lv, int lt, i
                 // stage offset: 3 * (sum of the Ns of the earlier radix-8 stages that have twiddles, i.e. Ns > 1)
                 const double2* tws = tw + 3 * (((1 << lgNs) - (1 << lead)) / 7 - (lead == 0 ? 1 : 0)) + jlo;
                 const double2 w1 = SIMT_LDG(tws);
-#ifdef MGVI_TW_SQUARE
-                // experiment: one table load per stage, W^2j and W^4j by
-                // squaring -- 2 L1 wavefront groups less per stage for 8 more FP64 instructions;
-                // costs <= 2 ulp on the twiddles
+#ifndef MGVI_TW_TABLE
+                // one table load per stage, W^2j and W^4j by squaring: 2 L1 wavefront groups less per stage
+                // for 8 more FP64 instructions on a pipe that is 40 % busy; costs <= 2 ulp on the twiddles.
+                // Measured on B200 (profiles/README.md, round 2): axis0_fused 0.90 -> 0.84 ms, C3 iteration
+                // 3.553 -> 3.488 ms.  -DMGVI_TW_TABLE restores the three table loads.
                 const double2 w2 = cmul(w1, w1);
 #else
                 const double2 w2 = SIMT_LDG(tws + (1 << lgNs));
@@ -158,7 +159,7 @@ SIMT_DEVICE void fft_line_forward(double2 (&v)[8], const LineView& lv, int lt, i
                 v[2] = cmul(v[2], w2);
                 double2 w3 = cmul(w1, w2);
                 v[3] = cmul(v[3], w3);
-#ifdef MGVI_TW_SQUARE
+#ifndef MGVI_TW_TABLE
                 const double2 w4 = cmul(w2, w2);
 #else
                 const double2 w4 = SIMT_LDG(tws + (2 << lgNs));

@@ -64,11 +64,29 @@ struct FieldEngine : Engine {
     DevBuf qsum;                      // N
     DevBuf n_x, n_r, n_p, n_t;        // Newton CG state (single vector)
     DevBuf tmpA, tmpB;                // generic-path staging [nvec][N]
+    // replayable chunk of the sampler's lock-step CG iterations (sample_cg)
+    struct CgGraphKey {
+        const void *R, *r, *p, *t, *tile, *wt;
+        int nvec;
+        double atol, rtol;
+        long long itmax;
+        bool operator==(const CgGraphKey& o) const {
+            return R == o.R && r == o.r && p == o.p && t == o.t && tile == o.tile && wt == o.wt && nvec == o.nvec &&
+                   atol == o.atol && rtol == o.rtol && itmax == o.itmax;
+        }
+    };
+    static const int kCgChunk = 8;
+    rt_graph cg_graph{};
+    bool cg_graph_valid = false;
+    CgGraphKey cg_graph_key{};
+    int64_t cg_graph_launches = 0;
+    bool graphs_on = true;          // MGVIB200_GRAPH=0 launches every kernel from the host
     CgScalars ncg_sc;
     bool ncg_first = true;
     int h_ncg[2] = {0, 0};
 
     ~FieldEngine() override {
+        if (cg_graph_valid) rt_graph_destroy(cg_graph);
         DevBuf* all[] = {&A, &data, &w, &q, &wbar, &center, &w_tiled, &ws_tile, &ws_r, &ws_p, &ws_t, &pt_t, &gather, &sc_gather, &kl_red, &qsum, &n_x, &n_r,
                          &n_p, &n_t, &tmpA, &tmpB, &rws.partials, &rws.counters, &rws.red};
         for (auto* b : all) b->release();
@@ -118,6 +136,7 @@ struct FieldEngine : Engine {
         if (const char* e = getenv("MGVIB200_PREFETCH_EPI")) prefetch_epi = atoi(e);
         if (const char* e = getenv("MGVIB200_STAGE_VIN")) stage_vin = atoi(e);
         if (const char* e = getenv("MGVIB200_TILED")) tiled_mode = atoi(e);
+        if (const char* e = getenv("MGVIB200_GRAPH")) graphs_on = atoi(e) != 0;
         if (const char* e = getenv("MGVIB200_ROW_THREADS")) row_threads = std::max(32, atoi(e));
         if (getenv("MGVIB200_FORCE_GENERIC") && atoi(getenv("MGVIB200_FORCE_GENERIC"))) big = false;
         if (!fast)
@@ -665,29 +684,81 @@ struct FieldEngine : Engine {
             P.cg = sc;
             chain_adjoint<PRO_RHS, EPI_RHS>(P, nvec, ws_t.as<double>(), FIN_RHS, nullptr);
         }
-        // lock-step CG over all residual samples (Krylov.jl cg!)
+        // lock-step CG over all residual samples (Krylov.jl cg!).  Every per-iteration scalar
+        // (alpha, beta, gamma, active masks, iteration counts, the itmax stop) lives in device memory, so an
+        // iteration is a FIXED launch sequence: after the first one (p = r, no update of p) a chunk of
+        // kCgChunk iterations is captured into a CUDA graph once and replayed.  The host only polls the
+        // number of active samples, one chunk behind the launches, so the stream never drains; iterations
+        // launched past convergence are no-ops (every block of an inactive sample exits at once).
         int* h = ctx->h_pinned;
-        long long it = 0;
-        int poll = 1;
         h[0] = 1;
         rt_d2h(h, cgws.n_active.p, sizeof(int), ctx->stream);
         rt_sync(ctx->stream);
-        while (h[0] > 0 && it < itmax) {
-            for (int k = 0; k < poll && it < itmax; ++k, ++it) {
-                FieldPassParams P = base_params();
-                P.r = ws_r.as<double>(); P.p = ws_p.as<double>();
-                P.vin = ws_p.as<double>(); P.vin_ld = N;
-                P.out = ws_t.as<double>(); P.out_ld = N;
-                P.w = w.as<double>();
-                P.first_iter = (it == 0);
-                P.cg = sc;
-                P.mask_active = 1;
-                chain_metric<PRO_CG>(P, nvec, ws_t.as<double>(), FIN_CG_PAP, nullptr);
-                vec_cg_update(ctx, rws, sc, R, ws_r.as<double>(), ws_p.as<double>(), ws_t.as<double>(), N, nvec);
+        auto launch_iter = [&](bool first) {
+            FieldPassParams P = base_params();
+            P.r = ws_r.as<double>(); P.p = ws_p.as<double>();
+            P.vin = ws_p.as<double>(); P.vin_ld = N;
+            P.out = ws_t.as<double>(); P.out_ld = N;
+            P.w = w.as<double>();
+            P.first_iter = first ? 1 : 0;
+            P.cg = sc;
+            P.mask_active = 1;
+            chain_metric<PRO_CG>(P, nvec, ws_t.as<double>(), FIN_CG_PAP, nullptr);
+            vec_cg_update(ctx, rws, sc, R, ws_r.as<double>(), ws_p.as<double>(), ws_t.as<double>(), N, nvec);
+        };
+        long long it = 0;
+        if (h[0] > 0 && itmax > 0) {
+            launch_iter(true);
+            it = 1;
+            const bool use_graph = rt_has_graphs && graphs_on && !ctx->profile;
+            if (use_graph) {
+                const CgGraphKey key{R, ws_r.p, ws_p.p, ws_t.p, ws_tile.p, w_tiled.p, nvec, o.abstol, o.reltol, itmax};
+                if (!cg_graph_valid || !(key == cg_graph_key)) {
+                    if (cg_graph_valid) { rt_graph_destroy(cg_graph); cg_graph_valid = false; }
+                    const int64_t l0 = ctx->launches;
+                    rt_capture_begin(ctx->stream);
+                    try {
+                        for (int k = 0; k < kCgChunk; ++k) launch_iter(false);
+                        cg_graph = rt_capture_end(ctx->stream);
+                    } catch (...) {
+                        rt_capture_abort(ctx->stream);
+                        throw;
+                    }
+                    cg_graph_launches = ctx->launches - l0;
+                    ctx->launches = l0;
+                    cg_graph_key = key;
+                    cg_graph_valid = true;
+                }
             }
-            rt_d2h(h, cgws.n_active.p, sizeof(int), ctx->stream);
-            rt_sync(ctx->stream);
-            if (poll < 8) poll *= 2;
+            if (!use_graph) {
+                // host-launched iterations (emulator build, per-kernel profiling, MGVIB200_GRAPH=0): poll after
+                // 1, 2, 4, 8, 8, ... iterations
+                int poll = 1;
+                while (h[0] > 0 && it < itmax) {
+                    for (int k = 0; k < poll && it < itmax; ++k, ++it) launch_iter(false);
+                    rt_d2h(h, cgws.n_active.p, sizeof(int), ctx->stream);
+                    rt_sync(ctx->stream);
+                    if (poll < kCgChunk) poll *= 2;
+                }
+            } else {
+                int slot = 0;
+                bool pending = false;
+                const long long it_cap = itmax + 2 * kCgChunk;      // the device stops every sample at itmax by itself
+                while (true) {
+                    rt_graph_launch(cg_graph, ctx->stream);
+                    ctx->launches += cg_graph_launches;
+                    it += kCgChunk;
+                    rt_d2h(h + 16 * (1 + slot), cgws.n_active.p, sizeof(int), ctx->stream);
+                    rt_event_record(ctx->ev_poll[slot], ctx->stream);
+                    if (pending) {
+                        rt_event_sync(ctx->ev_poll[slot ^ 1]);
+                        if (h[16 * (1 + (slot ^ 1))] <= 0) break;
+                    }
+                    if (it >= it_cap) break;
+                    pending = true;
+                    slot ^= 1;
+                }
+            }
         }
         rt_event_record(ctx->ev1, ctx->stream);
         std::vector<int> hi(nvec);
@@ -766,6 +837,29 @@ struct FieldEngine : Engine {
         rt_memset(ncgws.n_active.p, 0, sizeof(int) * 4, ctx->stream);
         vec_cg_init(ctx, rws, ncg_sc, g, N, n_x.as<double>(), n_r.as<double>(), n_p.as<double>(), N, 1);
         ncg_first = true;
+    }
+
+    void ncg_set_state(const double* x, const double* r, const double* u, double res, double prev) override {
+        const size_t b = sizeof(double) * N;
+        n_x.ensure(b); n_r.ensure(b); n_p.ensure(b); n_t.ensure(b);
+        ncgws.ensure(1);
+        ncg_sc = ncgws.scalars(0.0, 1.4901161193847656e-08, N, CG_ITSOLVERS);
+        rt_d2d(n_x.p, x, b, ctx->stream);
+        rt_d2d(n_r.p, r, b, ctx->stream);
+        rt_d2d(n_p.p, u, b, ctx->stream);
+        // device form of the iterator state: gamma = residual^2, beta = residual^2 / prev^2 (what the previous
+        // update's scalar tail would have left, field_pass.h: FIN_CG_RR), the vector active, tolerance 0
+        const double hs[4] = {res * res, (res * res) / (prev * prev), res, 0.0};
+        const int hi[2] = {0, 1};
+        rt_h2d(ncgws.gamma.p, &hs[0], sizeof(double), ctx->stream);
+        rt_h2d(ncgws.beta.p, &hs[1], sizeof(double), ctx->stream);
+        rt_h2d(ncgws.rnorm.p, &hs[2], sizeof(double), ctx->stream);
+        rt_h2d(ncgws.eps.p, &hs[3], sizeof(double), ctx->stream);
+        rt_h2d(ncgws.iters.p, &hi[0], sizeof(int), ctx->stream);
+        rt_h2d(ncgws.active.p, &hi[1], sizeof(int), ctx->stream);
+        rt_h2d(ncgws.n_active.p, &hi[1], sizeof(int), ctx->stream);
+        rt_sync(ctx->stream);
+        ncg_first = false;
     }
 
     bool ncg_active() override {

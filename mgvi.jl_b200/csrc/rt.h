@@ -8,6 +8,8 @@
 #include <string.h>
 #include <stdlib.h>
 #include <string>
+#include <utility>
+#include <vector>
 #include "simt.h"
 
 namespace mgvi {
@@ -49,17 +51,51 @@ inline void rt_event_destroy(rt_event e) { cudaEventDestroy(e); }
 inline void rt_event_record(rt_event e, rt_stream s) { RT_CUDA(cudaEventRecord(e, s)); }
 inline double rt_event_ms(rt_event a, rt_event b) { float ms = 0; RT_CUDA(cudaEventSynchronize(b)); RT_CUDA(cudaEventElapsedTime(&ms, a, b)); return ms; }
 
+// opt-in to > 48 KB of dynamic shared memory is a per-(kernel, device) attribute: set it once per pair
+// (and again only if a larger size is asked for), not on every launch
+inline void rt_ensure_smem_attr(const void* fn, size_t smem) {
+    struct Key { const void* fn; int dev; };
+    static std::vector<std::pair<Key, size_t>> cache;       // a few dozen entries: linear scan
+    int dev = 0;
+    RT_CUDA(cudaGetDevice(&dev));
+    for (auto& e : cache)
+        if (e.first.fn == fn && e.first.dev == dev) {
+            if (e.second >= smem) return;
+            RT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            e.second = smem;
+            return;
+        }
+    RT_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cache.push_back({Key{fn, dev}, smem});
+}
+
 template <typename K, typename P>
 inline void rt_launch(K kernel, long long grid, int block, size_t smem, rt_stream s, const P& params) {
     if (grid <= 0) return;
     if (grid > 2147483647LL) throw RtError{"grid too large", 1};
-    // opt in to > 48 KB of dynamic shared memory; set on every such launch (the attribute is per
-    // device and per kernel, a cache keyed on the function type alone would be wrong for both)
-    if (smem > 48 * 1024)
-        RT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) rt_ensure_smem_attr((const void*)kernel, smem);
     kernel<<<(unsigned)grid, block, smem, s>>>(params);
     RT_CUDA(cudaGetLastError());
 }
+
+// CUDA graphs: a fixed launch sequence (several lock-step CG iterations -- every per-iteration scalar
+// lives in device memory, so the kernel parameters do not change) captured once and replayed
+typedef cudaGraphExec_t rt_graph;
+static const bool rt_has_graphs = true;
+inline void rt_capture_begin(rt_stream s) { RT_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal)); }
+inline rt_graph rt_capture_end(rt_stream s) {
+    cudaGraph_t g = nullptr;
+    RT_CUDA(cudaStreamEndCapture(s, &g));
+    cudaGraphExec_t e = nullptr;
+    cudaError_t rc = cudaGraphInstantiate(&e, g, 0);
+    cudaGraphDestroy(g);
+    RT_CUDA(rc);
+    return e;
+}
+inline void rt_capture_abort(rt_stream s) { cudaGraph_t g = nullptr; cudaStreamEndCapture(s, &g); if (g) cudaGraphDestroy(g); cudaGetLastError(); }
+inline void rt_graph_launch(rt_graph g, rt_stream s) { RT_CUDA(cudaGraphLaunch(g, s)); }
+inline void rt_graph_destroy(rt_graph g) { if (g) cudaGraphExecDestroy(g); }
+inline void rt_event_sync(rt_event e) { RT_CUDA(cudaEventSynchronize(e)); }
 
 #else  // ---------------------------------- emulation --------------------------------------------
 
@@ -112,6 +148,15 @@ inline rt_event rt_event_create() { return 0; }
 inline void rt_event_destroy(rt_event) {}
 inline void rt_event_record(rt_event, rt_stream) {}
 inline double rt_event_ms(rt_event, rt_event) { return 0.0; }
+
+typedef int rt_graph;
+static const bool rt_has_graphs = false;
+inline void rt_capture_begin(rt_stream) {}
+inline rt_graph rt_capture_end(rt_stream) { return 0; }
+inline void rt_capture_abort(rt_stream) {}
+inline void rt_graph_launch(rt_graph, rt_stream) {}
+inline void rt_graph_destroy(rt_graph) {}
+inline void rt_event_sync(rt_event) {}
 
 template <typename K, typename P>
 inline void rt_launch(K kernel, long long grid, int block, size_t smem, rt_stream, const P& params) {

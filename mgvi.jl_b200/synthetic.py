@@ -123,3 +123,51 @@ def dense_linear_config(m=16384, k=4096, n_residuals=32, *, sigma=0.5, seed_J=3,
                 Z=rng.standard_normal((n_residuals, k)).T,
                 Z1=rng.standard_normal((n_residuals, m)).T,
                 Z2=rng.standard_normal((n_residuals, k)).T)
+
+
+def tutorial_grid(n_data, xlim=(1851.0, 1962.0), grain=3, padding=80.0):
+    """`produce_bins` of docs/src/advanced_tutorial_lit.jl:84-103 in exact rational arithmetic: the
+    fine GP grid (bin centres), its bin width and the 0-based start index of every data bin."""
+    from fractions import Fraction as Fr
+    lo, hi = Fr(xlim[0]), Fr(xlim[1])
+    data_binsize = (hi - lo) / n_data
+    gp_binsize = data_binsize / grain
+    gp_dim = int(((hi - lo) + 2 * Fr(padding)) // gp_binsize)
+    left = right = (gp_dim - n_data) // 2
+    if (2 * left + n_data * grain) % 2 == 1:
+        left += 1
+    gp_left_xlim = lo - left * gp_binsize
+    gp_right_xlim = hi + right * gp_binsize
+
+    def rng(a, step, b):             # collect(a:step:b)
+        out, v = [], a
+        while v <= b:
+            out.append(v)
+            v += step
+        return out
+    xs = rng(gp_left_xlim + gp_binsize / 2, gp_binsize, lo) + rng(lo + gp_binsize / 2, gp_binsize, hi) + \
+        rng(hi + gp_binsize / 2, gp_binsize, gp_right_xlim)
+    n_left = len(rng(gp_left_xlim + gp_binsize / 2, gp_binsize, lo))
+    idxs = np.arange(n_left, n_left + n_data * grain, grain)      # Julia: left+1 : grain : left + n_data grain (1-based)
+    assert n_left == left
+    return np.array([float(x) for x in xs]), float(gp_binsize), idxs
+
+
+def hyper_field_config(counts, n_residuals=3, *, grain=3, padding=80.0, xlim=(1851.0, 1962.0), seed_start=1,
+                       seed_draws=42, start_scale=1.0):
+    """The coal-mining model of docs/src/advanced_tutorial_lit.jl (hyperparameter field + bin
+    aggregation + Poisson counts).  `counts`: disasters per data bin (tests/golden/coal_mining_counts.npz)."""
+    counts = np.asarray(counts, dtype=np.float64)
+    xs, binsize, idxs = tutorial_grid(counts.size, xlim, grain, padding)
+    N = xs.size
+    hd = 1.0 / N / binsize                                        # _GP_HARMONIC_DIST :106
+    i = np.arange(N, dtype=np.float64)
+    kd = np.abs(np.where(i <= N // 2, i, i - N)) * hd             # dist_array :157-172
+    n_theta = N + 2
+    center = start_scale * np.random.default_rng(seed_start).standard_normal(n_theta)
+    rng = np.random.default_rng(seed_draws)
+    return dict(kind="hyper", kdist=kd, scale=hd, data_idxs=idxs, grain=int(grain), binsize=binsize, data=counts,
+                a0=2.0 * grain, a1=0.9, l0=12.0 / grain ** 0.3, l1=1.0 / 15.0, center=center,
+                n_residuals=int(n_residuals), n_theta=n_theta, n_lambda=counts.size, gp_xs=xs,
+                Z1=rng.standard_normal((n_residuals, counts.size)).T, Z2=rng.standard_normal((n_residuals, n_theta)).T,
+                Z=rng.standard_normal((n_residuals, n_theta)).T)

@@ -26,7 +26,7 @@ __all__ = [
     "dht", "dht_matrix",
     "fisher_normal", "fisher_mvnormal_diag", "fisher_mvnormal_full", "fisher_exponential", "fisher_poisson",
     "fisher_blockdiag", "fisher_blockdiag_dense",
-    "FieldModel", "PolyModel", "DenseLinearModel",
+    "FieldModel", "PolyModel", "DenseLinearModel", "HyperFieldModel",
     "metric_apply", "sampler_rhs", "krylov_cg", "sample_residuals_cg", "residual_pushfwd_operator",
     "sample_residuals_dense", "mv_normal_logdensity", "posterior_loglike", "mean_neg_log_pstr",
     "kl_gradient", "mean_metric_apply", "itsolvers_cg_iterator", "strong_wolfe", "NewtonCGOpts",
@@ -429,6 +429,97 @@ class DenseLinearModel:
         return self.Jm.T @ ((self.data - self.Jm @ xi) / (self.sigma * self.sigma))
 
 
+class HyperFieldModel:
+    """The tutorial's model (docs/src/advanced_tutorial_lit.jl:194-307): a 1-D Gaussian process whose
+    amplitude spectrum depends on two hyperparameters, exponentiated, integrated over data bins and
+    observed through Poisson counts.
+
+        theta = [p1, p2, xi (N)]                               (PARIDX :153, hyperparameters FIRST)
+        ampl  = a0 exp(a1 p1),  corrlen = l0 exp(l1 p2)        (sqrt_kernel :198-203: a0 = 2 GRAIN, a1 = 0.9,
+                                                                l0 = 12 / GRAIN^0.3, l1 = 1/15)
+        A[k]  = ampl sqrt(2 pi corrlen) exp(-pi^2 d_k^2 corrlen^2)      (amplitude_spectrum :194-196)
+        s     = c H(A . xi),  c = _GP_HARMONIC_DIST            (gp_sample :253-256)
+        fine  = exp(s)                                         (poisson_gp_link :275-277)
+        Lambda_b = binsize sum_{j = idx_b .. idx_b + grain - 1} fine[j]   (agg_lambdas :286-294)
+        data_b ~ Poisson(Lambda_b)                             (model :301-307), Fisher 1/Lambda_b.
+
+    `data_idxs` are 0-based start indices of the data bins."""
+
+    def __init__(self, kdist, scale, data_idxs, grain, binsize, data, *, a0, a1, l0, l1):
+        self.kd = np.asarray(kdist, dtype=np.float64)
+        self.N = self.kd.size
+        self.c = float(scale)
+        self.idx = np.asarray(data_idxs, dtype=np.int64)
+        self.grain = int(grain)
+        self.binsize = float(binsize)
+        self.data = np.asarray(data, dtype=np.float64).reshape(self.idx.size)
+        self.a0, self.a1, self.l0, self.l1 = float(a0), float(a1), float(l0), float(l1)
+        self.n_theta = self.N + 2
+        self.n_lambda = self.idx.size
+        self.cols = self.idx[:, None] + np.arange(self.grain)[None, :]        # fine pixels of every bin
+
+    def amplitude(self, p):
+        ampl = self.a0 * math.exp(self.a1 * p[0])
+        cl = self.l0 * math.exp(self.l1 * p[1])
+        A = ampl * math.sqrt(2.0 * math.pi * cl) * np.exp(-(math.pi ** 2) * self.kd ** 2 * cl ** 2)
+        dA1 = self.a1 * A                                                     # dA/dp1
+        dA2 = A * (self.l1 * (0.5 - 2.0 * math.pi ** 2 * self.kd ** 2 * cl ** 2))   # dA/dp2
+        return A, dA1, dA2
+
+    def fine_rate(self, p):
+        A, _, _ = self.amplitude(p)
+        return np.exp(self.c * dht(A * p[2:]))
+
+    def agg(self, fine):
+        return self.binsize * fine[self.cols].sum(axis=1)
+
+    def lam(self, p):
+        return self.agg(self.fine_rate(np.asarray(p, dtype=np.float64)))
+
+    def linearize(self, p) -> Linearization:
+        p = np.asarray(p, dtype=np.float64)
+        A, dA1, dA2 = self.amplitude(p)
+        xi = p[2:]
+        fine = np.exp(self.c * dht(A * xi))
+        Lam = self.agg(fine)
+        F = 1.0 / Lam                                                         # information.jl:74-78
+        N, nb = self.N, self.n_lambda
+
+        def jvp(v):
+            t = self.c * dht(A * v[2:] + (v[0] * dA1 + v[1] * dA2) * xi)
+            return self.agg(fine * t)
+
+        def vjp(l):
+            z = np.zeros(N)
+            z[self.cols] = (self.binsize * l)[:, None] * fine[self.cols]
+            g = self.c * dht(z)
+            out = np.empty(N + 2)
+            out[0] = float(np.sum(dA1 * xi * g))
+            out[1] = float(np.sum(dA2 * xi * g))
+            out[2:] = A * g
+            return out
+
+        def dense():
+            J = np.zeros((nb, N + 2))
+            eye = np.eye(N + 2)
+            for j in range(N + 2):
+                J[:, j] = jvp(eye[:, j])
+            return J
+
+        return Linearization(N + 2, nb, F, jvp, vjp, dense)
+
+    def loglike(self, p):
+        Lam = self.lam(p)
+        d = self.data
+        return float(np.sum(d * np.log(Lam) - Lam - scipy.special.gammaln(d + 1.0)))
+
+    def grad_loglike(self, p):
+        p = np.asarray(p, dtype=np.float64)
+        lin = self.linearize(p)
+        Lam = 1.0 / lin.fisher
+        return lin.vjp(self.data / Lam - 1.0)
+
+
 # --------------------------------------------------------------------------------------------
 # Metric and residual samplers -- src/residual_samplers.jl
 # --------------------------------------------------------------------------------------------
@@ -570,11 +661,12 @@ def mean_metric_apply(model, R, xi, u, lins=None):
 # --------------------------------------------------------------------------------------------
 # Newton-CG -- src/newtoncg.jl
 # --------------------------------------------------------------------------------------------
-def itsolvers_cg_iterator(matvec, b, *, reltol=SQRT_EPS, abstol=0.0, maxiter=None):
+def itsolvers_cg_iterator(matvec, b, *, reltol=SQRT_EPS, abstol=0.0, maxiter=None, states=None):
     """IterativeSolvers `cg_iterator!(x, A, b; initially_zero=true)` (call site
     src/newtoncg.jl:120; algorithm SURVEY.md appendix A.2) as a Python generator: yields
     (k, x, residual) AFTER the k-th update, exactly when Julia's `enumerate(cgiterator)` runs
-    the loop body; `x` is updated in place."""
+    the loop body; `x` is updated in place.  `states` (a list, tests only) receives the iterator
+    state (x, r, u, residual, prev_residual) as it stands BEFORE every update."""
     b = np.asarray(b, dtype=np.float64)
     n = b.size
     if maxiter is None:
@@ -589,6 +681,8 @@ def itsolvers_cg_iterator(matvec, b, *, reltol=SQRT_EPS, abstol=0.0, maxiter=Non
     while True:
         if it >= maxiter or residual <= tol:
             return
+        if states is not None:
+            states.append((x.copy(), r.copy(), u.copy(), residual, prev_residual))
         beta = residual ** 2 / prev_residual ** 2
         u = r + beta * u
         c = matvec(u)
@@ -680,7 +774,8 @@ def _newton_step(model, R, x, step, f_prev, df_n, opts, f, gradf, tr, rec, force
     lins = [model.linearize(x + R[:, i]) for i in range(n)]     # Sigma_bar_inv(x_n), :120
     dx = np.zeros_like(x)
     updates = 0
-    it = itsolvers_cg_iterator(lambda u: mean_metric_apply(model, R, x, u, lins), g)
+    it = itsolvers_cg_iterator(lambda u: mean_metric_apply(model, R, x, u, lins), g,
+                               states=rec["cg_states"] if rec is not None else None)
     if step == 1:
         for k, xk, _res in it:                   # :121-127
             dx, updates = xk, k
@@ -726,7 +821,7 @@ def _newton_step(model, R, x, step, f_prev, df_n, opts, f, gradf, tr, rec, force
 
 def _new_record(step, x, f_prev, df_n):
     return dict(step=step, x_n=x.copy(), f_prev=f_prev, df_n=df_n, dx_iters=[], f_k=[], cg_resid=[],
-                exit_margin=[], ls=[])
+                exit_margin=[], ls=[], cg_states=[])
 
 
 def newtoncg_optimize(model, R, x0, opts: NewtonCGOpts = NewtonCGOpts(), record: list | None = None):

@@ -55,5 +55,4 @@ def pytest_terminal_summary(terminalreporter):
     tr = terminalreporter
     tr.write_sep("-", "Newton-phase parity regimes (config -> regime, worst relative error)")
     for label, regime, worst in helpers.PARITY_LOG:
-        tr.write_line("  %-34s %-16s %.2e" % (label, regime.split(" (")[0], worst) + (
-            "  [" + regime.split(" (", 1)[1].rstrip(")") + "]" if " (" in regime else ""))
+        tr.write_line("  %-30s %s" % (label, regime if regime != "strict" else "strict (free-running end to end) %.1e" % worst))
