@@ -66,8 +66,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full-step", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-samples", type=int, default=4)
+    ap.add_argument("--ref-samples", type=int, default=0, help="CPU arm: residuals per step; 0 = one per host core")
     ap.add_argument("--ref-iters", type=int, default=2)
+    ap.add_argument("--no-configs", action="store_true", help="skip the short C1/C2/C4/C5 measurements")
     return ap.parse_args()
 
 
@@ -157,31 +158,84 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU restatement of the reference path (oracle/), timed on the host cores
+# CPU restatement of the reference path (oracle/), timed on the host cores.
+# The reference parallelises over residual samples (`Threads.@threads`, src/residual_samplers.jl:85-92):
+# one residual per core.  Here: one PROCESS per core (immune to torchrun's OMP_NUM_THREADS=1 and to the
+# GIL), each solving its own residual with single-threaded FFTs; a step is one lock-step round of all
+# workers (barrier at the start of every round), timed from the first start to the last finish.
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_rate(cfg, n_samples, iters, repeats=1, warmup=0):
-    """sample-iterations/s of the CPU restatement of MGVI.jl's CG sampler (oracle/, NumPy +
-    scipy.fft on all host cores) on a bounded sample of the workload: `n_samples` residuals x
-    `iters` CG iterations.  Returns (rate, seconds per repeat list, cores)."""
-    import oracle as O
+def _cpu_worker(widx, workload, field_std, sample_ids, iters, rounds, barrier, queue):
+    try:
+        os.environ["OMP_NUM_THREADS"] = "1"
+        os.environ["MKL_NUM_THREADS"] = "1"
+        os.environ["OPENBLAS_NUM_THREADS"] = "1"
+        sys.path.insert(0, ROOT)
+        import oracle as O
+        g = __import__("__graft_entry__")
+        syn = g.load_package().synthetic
+        dims, like, n = WORKLOADS[workload]
+        cfg = syn.field_config(dims, getattr(syn, like), n, field_std=field_std, draws=False)
+        O.mgvi_oracle.set_fft_workers(1)
+        om = O.FieldModel(cfg["dims"], cfg["amplitude"], cfg["scale"], cfg["data"], offset=cfg["offset"],
+                          link=cfg["link"], likelihood=cfg["likelihood"], sigma=cfg["sigma"], layout=cfg["layout"])
+        Z1 = np.empty((cfg["n_lambda"], len(sample_ids)))
+        Z2 = np.empty((cfg["n_theta"], len(sample_ids)))
+        for j, i in enumerate(sample_ids):
+            Z1[:, j], Z2[:, j] = draws_for(cfg, i)
+        spans = []
+        for _ in range(rounds):
+            barrier.wait()
+            t0 = time.time()
+            _R, it, _ = O.sample_residuals_cg(om, cfg["center"], Z1, Z2, atol=0.0, rtol=0.0, itmax=iters)
+            t1 = time.time()
+            assert int(it.sum()) == len(sample_ids) * iters
+            spans.append((t0, t1))
+        queue.put((widx, spans, None))
+    except BaseException as e:      # noqa: BLE001
+        try:
+            barrier.abort()
+        except Exception:           # noqa: BLE001
+            pass
+        queue.put((widx, [], repr(e)))
+
+
+def cpu_reference_rate(args, n_samples, iters, repeats=1, warmup=0):
+    """sample-iterations/s of the CPU restatement of MGVI.jl's CG sampler (oracle/) on a bounded sample of
+    the workload: `n_samples` residuals (default: one per host core) x `iters` CG iterations per step, one
+    worker process per core.  Returns (rate, seconds per step list, workers)."""
+    import multiprocessing as mp
     cores = os.cpu_count() or 1
-    O.mgvi_oracle.set_fft_workers(cores)
-    om = O.FieldModel(cfg["dims"], cfg["amplitude"], cfg["scale"], cfg["data"], offset=cfg["offset"],
-                      link=cfg["link"], likelihood=cfg["likelihood"], sigma=cfg["sigma"], layout=cfg["layout"])
-    Z1 = np.empty((cfg["n_lambda"], n_samples))
-    Z2 = np.empty((cfg["n_theta"], n_samples))
-    for i in range(n_samples):
-        Z1[:, i], Z2[:, i] = draws_for(cfg, i)
+    n_tot = WORKLOADS[args.workload][2]
+    if n_samples <= 0:
+        n_samples = max(1, min(cores, n_tot))
+    workers = max(1, min(cores, n_samples))
+    ids = [list(range(w, n_samples, workers)) for w in range(workers)]
+    ctxm = mp.get_context("spawn")          # the GPU arm has CUDA initialised: never fork it
+    barrier = ctxm.Barrier(workers)
+    queue = ctxm.Queue()
+    rounds = warmup + repeats
+    procs = [ctxm.Process(target=_cpu_worker, args=(w, args.workload, args.field_std, ids[w], iters, rounds, barrier, queue))
+             for w in range(workers)]
+    for p_ in procs:
+        p_.start()
+    got = [queue.get() for _ in procs]
+    for p_ in procs:
+        p_.join()
+    errs = [e for _, _, e in got if e]
+    if errs:
+        raise RuntimeError("CPU reference worker failed: " + errs[0])
     times = []
-    for rep in range(warmup + repeats):
-        t0 = time.perf_counter()
-        _R, it, _ = O.sample_residuals_cg(om, cfg["center"], Z1, Z2, atol=0.0, rtol=0.0, itmax=iters)
-        dt = time.perf_counter() - t0
-        assert int(it.sum()) == n_samples * iters
-        if rep >= warmup:
-            times.append(dt)
+    for r in range(warmup, rounds):
+        t0 = min(sp[r][0] for _, sp, _ in got)
+        t1 = max(sp[r][1] for _, sp, _ in got)
+        times.append(t1 - t0)
     rate = n_samples * iters * len(times) / sum(times)
-    return rate, times, cores
+    return rate, times, workers, n_samples
+
+
+CPU_NOTE = ("CPU restatement of MGVI.jl v0.4.5 hot path (oracle/: NumPy + scipy.fft), one residual sample per worker "
+            "process, one process per host core (the reference's Threads.@threads over samples, "
+            "src/residual_samplers.jl:85-92); Julia is not installed in this image")
 
 
 def run_reference(args, rank, world):
@@ -191,20 +245,29 @@ def run_reference(args, rank, world):
     syn = g.load_package().synthetic
     cfg = make_config(args, syn)
     K, W = args.steps, max(args.warmup, 1)
-    rate, times, cores = cpu_reference_rate(cfg, args.ref_samples, args.ref_iters, repeats=K, warmup=W)
-    sample = "%d residual samples x %d CG iterations per step (%s, full field size)" % (
-        args.ref_samples, args.ref_iters, args.workload)
+    rate, times, workers, ns = cpu_reference_rate(args, args.ref_samples, args.ref_iters, repeats=K, warmup=W)
+    sample = "%d residual samples x %d CG iterations per step (%s, full field size), %d worker processes" % (
+        ns, args.ref_iters, args.workload, workers)
     line = {
         "impl": "reference", "metric": metric_name(args), "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
         "warmup": W, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args, cfg), "field_std": args.field_std},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "note": "CPU restatement of MGVI.jl v0.4.5 hot path (NumPy + scipy.fft, all host cores); "
-                                 "Julia is not installed in this image"},
+        "config": bench_config(args, cfg, cfg["n_residuals"] // max(world, 1), world),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count(), "note": CPU_NOTE},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(json.dumps(line))
+
+
+def bench_config(args, cfg, n_loc, world):
+    """The `config` object both arms print (same keys, so the driver can compare them)."""
+    N, d = cfg["n_theta"], len(cfg["dims"])
+    B_cg = 32 * N * (d + 1) + 72 * N
+    return {"workload": workload_name(args, cfg), "iters_per_step": args.iters_per_step, "field_std": args.field_std,
+            "samples_per_gpu": n_loc, "parallelism": "sample-sharded x%d" % world,
+            "l2": "inputs larger than L2 (%.1f GB streamed per step per GPU)" % (B_cg * n_loc * args.iters_per_step / 1e9),
+            "timing": "CUDA events on the library stream, max over ranks"}
 
 
 def workload_name(args, cfg):
@@ -212,6 +275,192 @@ def workload_name(args, cfg):
     like = "Normal(sigma=%.2g)" % cfg["sigma"] if cfg["likelihood"] == 0 else "Poisson"
     return "%s: %s correlated field, %s, exp link, %d residual samples" % (args.workload, dims, like,
                                                                          cfg["n_residuals"])
+
+
+# ------------------------------------------------------------------------------------------------
+# Short measurements of the other BASELINE.json configurations (the `configs` block of the line)
+# ------------------------------------------------------------------------------------------------
+def _prof(ctx, fn):
+    lib = ctx.lib
+    lib.profile_begin(ctx.handle)
+    out = fn()
+    tags = (C.c_int32 * 64)(); ms = (C.c_double * 64)(); cnt = (C.c_int64 * 64)()
+    n = lib.profile_end(ctx.handle, 64, tags, ms, cnt)
+    return out, {int(tags[i]): (float(ms[i]), int(cnt[i])) for i in range(max(n, 0))}
+
+
+def quick_field(pkg, ctx, workload, n_loc, first_sample, iters, steps, warmup, hbm_peak, field_std):
+    """`steps` timed solves of `iters` lock-step CG iterations over n_loc residual samples, inputs resident."""
+    syn, lib = pkg.synthetic, ctx.lib
+    dims, like, n_tot = WORKLOADS[workload]
+    cfg = syn.field_config(dims, getattr(syn, like), n_tot, field_std=field_std, draws=False)
+    N, nl, d = cfg["n_theta"], cfg["n_lambda"], len(dims)
+    model = pkg.CorrelatedFieldModel.from_config(cfg, ctx)
+    Z1h, Z2h = np.empty((n_loc, nl)), np.empty((n_loc, N))
+    for j in range(n_loc):
+        Z1h[j], Z2h[j] = draws_for(cfg, first_sample + j)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    center = np.ascontiguousarray(cfg["center"])
+    bufs = [lib.dev_alloc(ctx.handle, b) for b in (8 * N, Z1h.nbytes, Z2h.nbytes, 8 * N * n_loc)]
+    c_dev, z1_dev, z2_dev, r_dev = bufs
+    ctx.check(lib.memcpy_h2d(ctx.handle, c_dev, vp(center), 8 * N))
+    ctx.check(lib.memcpy_h2d(ctx.handle, z1_dev, vp(Z1h), Z1h.nbytes))
+    ctx.check(lib.memcpy_h2d(ctx.handle, z2_dev, vp(Z2h), Z2h.nbytes))
+    ctx.check(lib.linearize_dev(model.handle, c_dev))
+    it = np.zeros(n_loc, dtype=np.int64)
+    rn = np.zeros(n_loc)
+    fixed = pkg.capi.CGOpts(0.0, 0.0, iters)
+
+    def step():
+        ctx.check(lib.sample_residuals_cg_dev(model.handle, z1_dev, z2_dev, n_loc, C.byref(fixed), r_dev,
+                                              it.ctypes.data_as(pkg.capi.c_int64_p), pkg.capi.ptr(rn)))
+        return ctx.last_timing()["sampler_ms"]
+
+    for _ in range(warmup):
+        step()
+    ms = sum(step() for _ in range(steps))
+    per_iter = ms / (steps * iters)
+    B_cg = 32 * N * (d + 1) + 72 * N
+    out = {"workload": workload_name(type("A", (), {"workload": workload})(), dict(cfg, n_residuals=n_tot)),
+           "samples_on_this_gpu": n_loc, "iters_per_step": iters, "steps": steps,
+           "value": n_loc * iters * steps / (ms * 1e-3), "unit": UNIT, "lockstep_iteration_ms": per_iter,
+           "B_cg_bytes_per_sample_iteration": B_cg,
+           "frac_of_hbm_peak": B_cg * n_loc / (per_iter * 1e-3) / 1e9 / hbm_peak}
+    if N * 8 * 4 * n_loc < 100e6:
+        out["note"] = "working set fits L2: latency-bound, the HBM fraction is not a roofline statement"
+    for b in bufs:
+        lib.dev_free(ctx.handle, b)
+    model.close()
+    return out
+
+
+def quick_poly(pkg, ctx):
+    """C1: the polynomial fit on the 1000-point grids, 8 residuals: whole mgvi_step through the host API."""
+    cfg = pkg.synthetic.polyfit_config(8, reference_grid=False)
+    m = pkg.model_from_config(cfg, ctx)
+    conf = pkg.MGVIConfig()
+    pkg.mgvi_step(m, cfg["data"], 8, cfg["center"], conf, ctx, draws=(cfg["Z1"], cfg["Z2"]))
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        res, _c = pkg.mgvi_step(m, cfg["data"], 8, cfg["center"], conf, ctx, draws=(cfg["Z1"], cfg["Z2"]))
+    dt = (time.perf_counter() - t0) / reps
+    m.close()
+    return {"workload": "c1: polynomial fit, Normal, 5 parameters, 1000 data points, 8 residual samples (CG sampler + NewtonCG)",
+            "mgvi_step_ms": dt * 1e3, "steps_per_s": 1.0 / dt, "mnlp": res.mnlp, "note": "latency-bound: time only"}
+
+
+def quick_dense(pkg, ctx, torch):
+    """C4: dense J 16384 x 4096, MatrixInversion sampler.  The FP64 tensor-pipe denominator is measured here:
+    cuBLAS dgemm (torch.mm, float64) of the same full product, and cuSOLVER's Cholesky of the same matrix."""
+    mm, k, n = 16384, 4096, 32
+    cfg = pkg.synthetic.dense_linear_config(mm, k, n)
+    model, prof_c = _prof(ctx, lambda: pkg.model_from_config(cfg, ctx))
+    syrk_ms = prof_c.get(3001, (0.0, 0))[0]
+    pkg.ResidualSampler(model, cfg["center"], pkg.MatrixInversion(), ctx)
+    Z = np.asfortranarray(cfg["Z"])
+    R = np.empty((k, n), order="F")
+
+    def run():
+        ctx.check(ctx.lib.sample_residuals_dense(model.handle, pkg.capi.ptr(Z), n, pkg.capi.ptr(R), None))
+    _, p1 = _prof(ctx, run)          # factorises
+    _, p2 = _prof(ctx, run)          # factor kept
+    chol_ms = sum(v[0] for v in p1.values()) - sum(v[0] for v in p2.values())
+    conf = pkg.MGVIConfig(linsolver=pkg.MatrixInversion())
+    pkg.mgvi_step(model, cfg["data"], n, cfg["center"], conf, ctx, draws=cfg["Z"])
+    t0 = time.perf_counter()
+    res, _c = pkg.mgvi_step(model, cfg["data"], n, cfg["center"], conf, ctx, draws=cfg["Z"])
+    step_s = time.perf_counter() - t0
+    model.close()
+    # denominators (library code, measured on this box, never on the product path)
+    Jt = torch.from_numpy(cfg["J"]).cuda()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        Mt = torch.mm(Jt.T, Jt)
+    torch.cuda.synchronize()
+    e0.record()
+    reps = 3
+    for _ in range(reps):
+        Mt = torch.mm(Jt.T, Jt)
+    e1.record(); torch.cuda.synchronize()
+    dgemm_ms = e0.elapsed_time(e1) / reps
+    Mt = Mt * 4.0 + torch.eye(k, dtype=torch.float64, device="cuda")
+    torch.linalg.cholesky(Mt)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        torch.linalg.cholesky(Mt)
+    e1.record(); torch.cuda.synchronize()
+    potrf_ms = e0.elapsed_time(e1) / reps
+    del Jt, Mt
+    torch.cuda.empty_cache()
+    full = 2.0 * mm * k * k
+    T = (k + 127) // 128
+    executed = 2.0 * mm * 128 * 128 * (T * (T + 1) // 2)        # upper block tiles only
+    dgemm_tf = full / (dgemm_ms * 1e-3) / 1e12
+    ours_tf = executed / (syrk_ms * 1e-3) / 1e12 if syrk_ms else None
+    return {"workload": "c4: dense J %d x %d, Normal(0.5), %d residuals, MatrixInversion sampler" % (mm, k, n),
+            "syrk_ms": syrk_ms, "syrk_tflops_executed": ours_tf,
+            "syrk_full_product_equivalent_tflops": full / (syrk_ms * 1e-3) / 1e12 if syrk_ms else None,
+            "cublas_dgemm_full_product_ms": dgemm_ms, "cublas_dgemm_tflops": dgemm_tf,
+            "roofline": {"bound": "tensor", "kernel": "k_dmma_gemm (J'FJ, upper block tiles, mma.sync m8n8k4 f64)",
+                         "achieved": ours_tf, "peak": dgemm_tf, "unit": "TFLOP/s",
+                         "frac": (ours_tf / dgemm_tf) if ours_tf else None,
+                         "peak_source": "cuBLAS dgemm 16384 x 4096 x 4096 (torch.mm, float64) measured in this run"},
+            "cholesky_ms": chol_ms, "cusolver_potrf_ms": potrf_ms,
+            "cholesky_tflops": (k ** 3 / 3.0) / (chol_ms * 1e-3) / 1e12 if chol_ms > 0 else None,
+            "sample_ms_after_factor": sum(v[0] for v in p2.values()), "mgvi_step_s": step_s, "mnlp": res.mnlp}
+
+
+def c5_step(pkg, ctx, rank, world, per_gpu, sampler_maxiters, torch, dist, field_std):
+    """BASELINE.json configs[4] at `per_gpu` residual samples per GPU (8 per GPU = 64 on 8 GPUs; weak scaling in
+    N): one mgvi_step through the host-buffer C ABI -- sampler capped at `sampler_maxiters` lock-step iterations
+    (a converged C5 sampler is thousands of iterations and has no communication), then the complete default
+    NewtonCG phase, whose KL value / gradient / mean-weight sums cross the GPUs."""
+    syn, lib = pkg.synthetic, ctx.lib
+    dims, like, _n = WORKLOADS["c5"]
+    n_tot = per_gpu * world
+    cfg = syn.field_config(dims, getattr(syn, like), n_tot, field_std=field_std, draws=False)
+    N, nl = cfg["n_theta"], cfg["n_lambda"]
+    model = pkg.CorrelatedFieldModel.from_config(cfg, ctx)
+    Z1h, Z2h = np.empty((per_gpu, nl)), np.empty((per_gpu, N))
+    for j in range(per_gpu):
+        Z1h[j], Z2h[j] = draws_for(cfg, rank * per_gpu + j)
+    samples = np.empty((2 * per_gpu, N))
+    c_out = np.empty(N)
+    mnlp = C.c_double()
+    trace = pkg.capi.NewtonCGTrace()
+    iters = np.zeros(per_gpu, dtype=np.int64)
+    cg = pkg.capi.CGOpts(pkg.api.SQRT_EPS, pkg.api.SQRT_EPS, int(sampler_maxiters))
+    opts = pkg.capi.NewtonCGOpts(0.1, 4, 5, 50)
+    center = np.ascontiguousarray(cfg["center"])
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sync()
+    t0 = time.perf_counter()
+    ctx.check(lib.step(model.handle, pkg.capi.ptr(center), pkg.capi.ptr(Z1h), pkg.capi.ptr(Z2h), per_gpu, 0,
+                       C.byref(cg), C.byref(opts), pkg.capi.ptr(samples), pkg.capi.ptr(c_out), C.byref(mnlp),
+                       iters.ctypes.data_as(pkg.capi.c_int64_p), C.byref(trace)))
+    sync()
+    dt = time.perf_counter() - t0
+    tm = ctx.last_timing()
+    red = torch.tensor([dt, tm["sampler_ms"], tm["newton_ms"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+    model.close()
+    tr = trace.as_dict()
+    return {"workload": "c5: 256x256x256 correlated field, Poisson, exp link, %d residual samples (%d per GPU)" % (n_tot, per_gpu),
+            "scaling": "weak", "n_gpus": world, "seconds": float(red[0]), "steps_per_s": 1.0 / float(red[0]),
+            "sampler_ms": float(red[1]), "sampler_lockstep_iterations_cap": int(sampler_maxiters),
+            "newton_ms": float(red[2]), "newton_phases_per_s": 1e3 / float(red[2]), "mnlp": float(mnlp.value),
+            "kl_evaluations": tr["f_calls"], "kl_gradients": tr["g_calls"], "newton_cg_updates": tr["cg_updates"],
+            "collectives": "all-gather of canonical chunk partials per KL value / gradient / mean weight (NCCL)" if world > 1 else "none (1 GPU)",
+            "h2d_bytes": int(Z1h.nbytes + Z2h.nbytes + center.nbytes), "d2h_bytes": int(samples.nbytes + c_out.nbytes)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -366,21 +615,13 @@ def main():
         k["share"] = k["avg_ms"] * k["launches"] / tot_ms
     kern.sort(key=lambda k: -k["share"])
     dom = kern[0] if kern else None
-    # DRAM bytes per launch of each kernel from the committed `ncu --set full` capture of this same
-    # workload (profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum, 32 samples)
-    traffic = {}
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload, {})
-    except Exception:
-        pass
-    for k_ in kern:
-        t_ = traffic.get(str(k_["tag"]))
-        k_["dram_traffic_bytes_per_launch"] = (t_ * n_loc / 32.0) if (t_ and world >= 1) else None
     roofline = None
     if dom and "algorithmic_gbs" in dom:
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["algorithmic_gbs"], "peak": hbm_peak,
                     "unit": "GB/s", "frac": dom["algorithmic_gbs"] / hbm_peak,
-                    "traffic": dom.get("dram_traffic_bytes_per_launch"),
+                    "traffic": None,
+                    "traffic_note": "not measurable inside a timed run; the ncu --set full capture of this command is "
+                                    "profiles/r2_ncu_full_c3_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
                     "peak_source": peak_src, "share_of_step": dom["share"],
                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"]}
     # the whole Fisher-CG iteration against B_cg: what north_star's 60 % target is about
@@ -388,15 +629,18 @@ def main():
     cg_path = {"B_cg_bytes_per_sample_iteration": ab["B_cg"], "lockstep_iteration_ms": per_iter_ms,
                "achieved_gbs": ab["B_cg"] * n_loc / (per_iter_ms * 1e-3) / 1e9}
     cg_path["frac_of_hbm_peak"] = cg_path["achieved_gbs"] / hbm_peak
+    if d >= 2:
+        # bytes the kernels actually move per sample-iteration: 32N + 16N (+ 32N per middle
+        # axis) + 24N + 48N -- A and w are shared by all samples and stay in L2
+        moved = (120 + 32 * (d - 2)) * N
+        cg_path["bytes_moved_per_sample_iteration"] = moved
+        cg_path["frac_of_hbm_peak_bytes_moved"] = moved * n_loc / (per_iter_ms * 1e-3) / 1e9 / hbm_peak
 
     out = {
         "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args, cfg), "iters_per_step": ITERS, "field_std": args.field_std,
-                   "samples_per_gpu": n_loc, "parallelism": "sample-sharded x%d" % world,
-                   "l2": "inputs larger than L2 (%.1f GB streamed per step per GPU)" % (ab["B_cg"] * n_loc * ITERS / 1e9),
-                   "timing": "CUDA events on the library stream, max over ranks"},
+        "config": bench_config(args, cfg, n_loc, world),
         "wall_ms_per_step": wall_ms_max / K,
         "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cg_path": cg_path,
         "kernels": kern,
@@ -454,19 +698,44 @@ def main():
                             "sampler_ms": tm["sampler_ms"], "newton_ms": tm["newton_ms"],
                             "sampler_iterations": int(iters.sum()), "trace": trace.as_dict()}
 
+    # ---- the other BASELINE.json configurations, short (rank 0 of a single-GPU run) -------------------
+    free_main = False
+    if not args.no_configs and args.workload == "c3":
+        for p in (c_dev, z1_dev, z2_dev, r_dev):
+            lib.dev_free(ctx.handle, p)
+        model.close()
+        free_main = True
+        cfgs = {}
+        if world == 1:
+            for name, fn in (("c1", lambda: quick_poly(pkg, ctx)),
+                             ("c2", lambda: quick_field(pkg, ctx, "c2", 16, 0, 200, 3, 2, hbm_peak, args.field_std)),
+                             ("c4", lambda: quick_dense(pkg, ctx, torch)),
+                             ("c5", lambda: quick_field(pkg, ctx, "c5", 8, 0, 10, 2, 1, hbm_peak, args.field_std))):
+                try:
+                    cfgs[name] = fn()
+                except Exception as e:      # noqa: BLE001
+                    cfgs[name] = {"error": repr(e)}
+        # every N: one C5 mgvi_step with the Newton phase (the phase that communicates), 8 samples per GPU
+        try:
+            cfgs["c5_step"] = c5_step(pkg, ctx, rank, world, 8, 30, torch, dist, args.field_std)
+        except Exception as e:              # noqa: BLE001
+            cfgs["c5_step"] = {"error": repr(e)}
+        out["configs"] = cfgs
+
     # ---- CPU baseline beside it (rank 0, single-GPU run only) ----------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, times, cores = cpu_reference_rate(cfg, args.ref_samples, args.ref_iters, repeats=1, warmup=0)
-        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": "%d residual samples x %d CG iterations at full field size (%.1f s)" % (
-                                   args.ref_samples, args.ref_iters, sum(times)),
-                               "note": "CPU restatement of MGVI.jl v0.4.5 hot path (oracle/: NumPy + scipy.fft, "
-                                       "all host cores); Julia is not installed in this image"}
+        rate, times, workers, ns = cpu_reference_rate(args, args.ref_samples, args.ref_iters, repeats=2, warmup=1)
+        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": workers, "kind": "port",
+                               "host_cores": os.cpu_count(),
+                               "sample": "%d residual samples x %d CG iterations at full field size, %d worker "
+                                         "processes (%.1f s per step)" % (ns, args.ref_iters, workers, float(np.mean(times))),
+                               "note": CPU_NOTE}
     if rank == 0:
         emit(json.dumps(out))
-    for p in (c_dev, z1_dev, z2_dev, r_dev):
-        lib.dev_free(ctx.handle, p)
-    model.close()
+    if not free_main:
+        for p in (c_dev, z1_dev, z2_dev, r_dev):
+            lib.dev_free(ctx.handle, p)
+        model.close()
     if world > 1:
         dist.destroy_process_group()
 

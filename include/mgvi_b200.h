@@ -46,6 +46,7 @@ typedef struct mgvib200_model mgvib200_model;
 #define MGVIB200_MODEL_FIELD_DHT 0     /* test/test_models/model_fft_gp.jl, docs/src/advanced_tutorial_lit.jl:253-307 */
 #define MGVIB200_MODEL_POLY 1          /* test/test_models/model_polyfit.jl */
 #define MGVIB200_MODEL_DENSE_LINEAR 2  /* dense Jacobian; operator type of MatrixInversion, src/residual_samplers.jl:56 */
+#define MGVIB200_MODEL_FIELD_HYPER 3   /* docs/src/advanced_tutorial_lit.jl:194-307: hyperparameter field + bin aggregation */
 
 #define MGVIB200_LINK_IDENTITY 0
 #define MGVIB200_LINK_EXP 1
@@ -83,6 +84,22 @@ typedef struct {
     /* ---- DENSE_LINEAR: mu = J xi, J is (m x k) column-major ---- */
     const double* J;
     int64_t m, k;
+    const double* sigma_vec;    /* optional per-datum noise level (m values); null: the constant `sigma`.
+                                   F = diag(1/sigma_i^2) is folded into the operand load of the J'FJ GEMM */
+    /* ---- FIELD_HYPER (docs/src/advanced_tutorial_lit.jl:194-307): a 1-D field (ndim = 1, dims[0] = N) whose
+     *      amplitude spectrum depends on two hyperparameters, exponentiated, integrated over data bins:
+     *        theta = [p1, p2, xi(N)]                          (PARIDX :153, hyperparameters first)
+     *        A[k]  = ampl sqrt(2 pi cl) exp(-pi^2 kdist[k]^2 cl^2),  ampl = hyper[0] exp(hyper[1] p1),
+     *                cl = hyper[2] exp(hyper[3] p2)           (amplitude_spectrum / sqrt_kernel :194-203)
+     *        s = scale * H(A . xi),  fine = exp(s)            (gp_sample :253-256, poisson_gp_link :275-277)
+     *        Lambda_b = binsize * sum_{t < grain} fine[bin_start + grain b + t],  b < n_data   (agg_lambdas :286-294)
+     *        data_b ~ Poisson(Lambda_b)                       (model :301-307)
+     *      n_theta = N + 2, n_lambda = n_data. ---- */
+    const double* kdist;        /* N harmonic distances (dist_array :157-172) */
+    double hyper[4];            /* a0, a1, l0, l1 */
+    int64_t bin_start;          /* 0-based index of the first fine pixel of data bin 0 */
+    int32_t grain;              /* fine pixels per data bin (GP_GRAIN_FACTOR) */
+    double binsize;             /* width of a fine pixel (_GP_BINSIZE) */
 } mgvib200_model_desc;
 
 /* NewtonCG (src/newtoncg.jl:14-31) */

@@ -6,7 +6,7 @@ The directory name is not a valid dotted module name; import it through
 from . import capi, synthetic
 from .capi import LIB_PATH, Library, MGVIB200Error
 from .api import *  # noqa: F401,F403
-from .api import (LBFGS, LBFGSB, KLObjective, newton_probe, ncg_probe, B200CG, B200Dense, B200NewtonCG, CorrelatedFieldModel, DenseLinearModel, FullJacobianFunc,
+from .api import (LBFGS, LBFGSB, KLObjective, newton_probe, ncg_probe, B200CG, B200Dense, B200NewtonCG, CorrelatedFieldModel, DenseLinearModel, HyperFieldModel, FullJacobianFunc,
                   FullResidualSampler, FwdDerJacobianFunc, FwdRevADJacobianFunc, ImplicitResidualSampler,
                   KrylovJL_CG, MatrixInversion, MGVIConfig, MGVIContext, MGVIResult, NewtonCG, PolynomialModel,
                   ResidualSampler, build_samples, fisher_information, kl_value_grad, mean_metric_apply,

@@ -34,7 +34,7 @@ from .capi import MGVIB200Error, as_f64, ptr
 
 SQRT_EPS = 1.4901161193847656e-08
 
-MODEL_FIELD_DHT, MODEL_POLY, MODEL_DENSE_LINEAR = 0, 1, 2
+MODEL_FIELD_DHT, MODEL_POLY, MODEL_DENSE_LINEAR, MODEL_FIELD_HYPER = 0, 1, 2, 3
 LINK_IDENTITY, LINK_EXP = 0, 1
 LIKE_NORMAL, LIKE_POISSON = 0, 1
 LAYOUT_MU_ONLY, LAYOUT_BLOCKED, LAYOUT_INTERLEAVED = 0, 1, 2
@@ -333,12 +333,19 @@ class DenseLinearModel(_Model):
     kind = MODEL_DENSE_LINEAR
 
     def __init__(self, J, data, context: MGVIContext, *, sigma=0.5, layout=LAYOUT_MU_ONLY):
+        """`sigma`: one noise level, or one per datum (m values) -- then F = diag(1/sigma_i^2) is folded
+        into the operand load of the J'FJ tensor-core GEMM."""
         super().__init__(context)
         J = as_f64(J)
         m, k = J.shape
         d = as_f64(data, (m,))
         desc = capi.ModelDesc()
         desc.kind = self.kind
+        sv = None
+        if np.ndim(sigma) > 0:
+            sv = as_f64(sigma, (m,))
+            desc.sigma_vec = ptr(sv)
+            sigma = float(sv[0])
         desc.likelihood, desc.sigma, desc.lambda_layout = LIKE_NORMAL, float(sigma), int(layout)
         desc.data, desc.n_data = ptr(d), m
         desc.J, desc.m, desc.k = ptr(J), m, k
@@ -350,9 +357,52 @@ class DenseLinearModel(_Model):
         return cls(cfg["J"], cfg["data"], context, sigma=cfg["sigma"], layout=cfg["layout"])
 
 
+class HyperFieldModel(_Model):
+    """The reference tutorial's model (docs/src/advanced_tutorial_lit.jl:194-307): a 1-D Gaussian process
+    whose amplitude spectrum depends on two hyperparameters (`sqrt_kernel` :198-203), exponentiated
+    (`poisson_gp_link` :275-277), integrated over data bins of `grain` fine pixels (`agg_lambdas`
+    :286-294) and observed through Poisson counts (`model` :301-307).
+
+        theta = [p1, p2, xi(N)];  A[k] = a0 e^{a1 p1} sqrt(2 pi cl) exp(-pi^2 kdist[k]^2 cl^2),  cl = l0 e^{l1 p2}
+        s = scale * H(A . xi);  Lambda_b = binsize * sum_{t < grain} exp(s)[bin_start + grain b + t]
+
+    `data_idxs`: 0-based first fine pixel of every data bin; must be regular (start + grain * b)."""
+    kind = MODEL_FIELD_HYPER
+
+    def __init__(self, kdist, scale, data_idxs, grain, binsize, data, context: MGVIContext, *, a0, a1, l0, l1):
+        super().__init__(context)
+        kd = as_f64(kdist)
+        N = kd.size
+        d = as_f64(data)
+        idx = np.asarray(data_idxs, dtype=np.int64).ravel()
+        if idx.size != d.size or idx.size < 1:
+            raise MGVIB200Error("HyperFieldModel: one start index per data bin")
+        if not np.array_equal(idx, idx[0] + int(grain) * np.arange(idx.size)):
+            raise MGVIB200Error("HyperFieldModel: data bins must be regular (start + grain * b), as produce_bins makes them")
+        desc = capi.ModelDesc()
+        desc.kind = self.kind
+        desc.ndim = 1
+        desc.dims[0] = N
+        desc.scale, desc.link, desc.likelihood = float(scale), LINK_EXP, LIKE_POISSON
+        desc.lambda_layout = LAYOUT_MU_ONLY
+        desc.data, desc.n_data = ptr(d), d.size
+        desc.kdist = ptr(kd)
+        for i, v in enumerate((a0, a1, l0, l1)):
+            desc.hyper[i] = float(v)
+        desc.bin_start, desc.grain, desc.binsize = int(idx[0]), int(grain), float(binsize)
+        self._create(desc)
+        self.dims = (N,)
+        self.data = d.ravel().copy()
+
+    @classmethod
+    def from_config(cls, cfg: dict, context: MGVIContext):
+        return cls(cfg["kdist"], cfg["scale"], cfg["data_idxs"], cfg["grain"], cfg["binsize"], cfg["data"], context,
+                   a0=cfg["a0"], a1=cfg["a1"], l0=cfg["l0"], l1=cfg["l1"])
+
+
 def model_from_config(cfg: dict, context: MGVIContext) -> _Model:
-    return {"field": CorrelatedFieldModel, "poly": PolynomialModel, "dense": DenseLinearModel}[cfg["kind"]] \
-        .from_config(cfg, context)
+    return {"field": CorrelatedFieldModel, "poly": PolynomialModel, "dense": DenseLinearModel,
+            "hyper": HyperFieldModel}[cfg["kind"]].from_config(cfg, context)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -28,6 +28,9 @@ class ModelDesc(C.Structure):
         ("n_groups", C.c_int32), ("group_sizes", c_int64_p), ("x", c_double_p), ("n_coef", C.c_int32),
         ("coef_scale", c_double_p), ("noise_scale", C.c_double),
         ("J", c_double_p), ("m", C.c_int64), ("k", C.c_int64),
+        ("sigma_vec", c_double_p),
+        ("kdist", c_double_p), ("hyper", C.c_double * 4), ("bin_start", C.c_int64), ("grain", C.c_int32),
+        ("binsize", C.c_double),
     ]
 
 

@@ -368,6 +368,7 @@ int mgvib200_model_create(mgvib200_ctx* ctx, const mgvib200_model_desc* d, mgvib
             case MGVIB200_MODEL_FIELD_DHT: e = make_field_engine(ctx, *d); break;
             case MGVIB200_MODEL_POLY: e = make_poly_engine(ctx, *d); break;
             case MGVIB200_MODEL_DENSE_LINEAR: e = make_dense_engine(ctx, *d); break;
+            case MGVIB200_MODEL_FIELD_HYPER: e = make_hyper_engine(ctx, *d); break;
             default: throw RtError{"unknown model kind", MGVIB200_ERR_INVALID};
         }
         mgvib200_model* m = new mgvib200_model();

@@ -152,41 +152,29 @@ SIMT_GLOBAL(128) k_tri_fill(SIMT_KARGS(TriParams)) { SIMT_SMEM_DECL (void)simt_s
 SIMT_GLOBAL(256) k_potrf(SIMT_KARGS(TriParams)) { SIMT_SMEM_DECL potrf_body(P, simt_smem); }
 SIMT_GLOBAL(64) k_trsolve(SIMT_KARGS(TriParams)) { SIMT_SMEM_DECL trsolve_body(P, simt_smem); }
 
-namespace {
-
-struct DenseEngine : Engine {
-    long long m = 0, k = 0;
-    double sigma = 1.0, inv_s2 = 1.0, dd = 0.0, const_term = 0.0;
-    int layout = 0;
-    long long z1_stride = 1;
-    DevBuf J, data, M, h, center, Mf, W, P2, MP, gsum, ws_r, ws_p, ws_t, n_x, n_r, n_p, n_t, Rinv;
+// MatrixInversion sampler (src/residual_samplers.jl:95-123) on a materialised symmetric metric M (k x k,
+// device memory): shared by the dense-linear engine and by the field engines' small-model dense path.
+struct DenseChol {
+    mgvib200_ctx* ctx = nullptr;
+    long long k = 0;
+    DevBuf Mf, W, Rinv;
     ReduceWs rws;
-    CgWs cgws, ncgws;
-    CgScalars ncg_sc;
-    bool ncg_first = true, have_chol = false;
-    int h_act = 0;
+    bool have_chol = false;
 
-    bool counted = false;
-    // "replicas only" (SURVEY.md 8e): mgvib200_comm_init refuses contexts that hold a dense model, setup()
-    // refuses a context that already has a communicator; this covers every entry point that would sum
-    // over residual samples
-    void single_rank_only() const {
-        if (ctx->world > 1) throw RtError{"DENSE_LINEAR: replicas only (SURVEY.md 8e); run one replica per GPU", 3};
-    }
-
-    ~DenseEngine() override {
-        if (counted) ctx->n_models_single_rank--;
-        DevBuf* all[] = {&J, &data, &M, &h, &center, &Mf, &W, &P2, &MP, &gsum, &ws_r, &ws_p, &ws_t, &n_x, &n_r, &n_p,
-                         &n_t, &Rinv, &rws.partials, &rws.counters, &rws.red};
+    void release() {
+        DevBuf* all[] = {&Mf, &W, &Rinv, &rws.partials, &rws.counters, &rws.red};
         for (auto* b : all) b->release();
+        have_chol = false;
     }
 
     void gemm(const double* A, long long a_row, long long a_k, const double* B, long long b_k, long long b_col,
-              double* C, long long ldc, int Mr, int Nc, int Kr, double alpha, double beta, bool upper_only = false) {
+              double* C, long long ldc, int Mr, int Nc, int Kr, double alpha, double beta, bool upper_only = false,
+              const double* kweight = nullptr) {
         if (Mr <= 0 || Nc <= 0) return;
         GemmParams g;
         g.A = A; g.a_row = a_row; g.a_k = a_k; g.B = B; g.b_k = b_k; g.b_col = b_col; g.C = C; g.ldc = ldc;
         g.M = Mr; g.N = Nc; g.K = Kr; g.alpha = alpha; g.beta = beta; g.upper_only = upper_only ? 1 : 0;
+        g.kweight = kweight;
         g.ntm = (Mr + kGemmBM - 1) / kGemmBM; g.ntn = (Nc + kGemmBN - 1) / kGemmBN;
         ctx->prof_pre(3000 + (upper_only ? 1 : 0));
         rt_launch(k_dmma_gemm, (long long)g.ntm * g.ntn, 256, sizeof(double) * 2 * kGemmBM * kGemmLd, ctx->stream, g);
@@ -218,6 +206,134 @@ struct DenseEngine : Engine {
         return P;
     }
 
+    // Mf = P M P = R'R, R upper, blocked right-looking; the factor stays in Mf (upper triangle)
+    void factorize(const double* M) {
+        if (have_chol) return;
+        Mf.ensure(8 * k * k);
+        // flip rows and columns: Mf[i][j] = M[k-1-i][k-1-j]; with M symmetric a flip of the flat array does it
+        VecParams P = vp();
+        P.op = VOP_FLIP; P.N = k * k; P.in = M; P.out = Mf.as<double>();
+        vec_launch(ctx, rws, P);
+        double* A = Mf.as<double>();
+        for (long long j0 = 0; j0 < k; j0 += kNb) {
+            const int nb = (int)std::min<long long>(kNb, k - j0);
+            tri(TRI_POTRF, A, k, nullptr, 0, (int)j0, nb, 0, 0, (int)k);
+            const int rest = (int)(k - j0 - nb);
+            if (rest > 0) {
+                tri(TRI_PANEL, A, k, A, k, (int)j0, nb, (int)(j0 + nb), rest, (int)k);
+                // trailing update A22 -= X'X, X = A[j0:j0+nb, j0+nb:]  (upper block tiles only)
+                const double* X = A + j0 + (j0 + nb) * k;
+                gemm(X, k, 1, X, 1, k, A + (j0 + nb) + (j0 + nb) * k, k, rest, rest, nb, -1.0, 1.0, true);
+            }
+        }
+        have_chol = true;
+    }
+
+    // X (k x ncols, leading dimension k) <- R^-1 X, blocked back substitution
+    void back_solve(double* X, int ncols) {
+        const double* A = Mf.as<double>();
+        const long long nblk = (k + kNb - 1) / kNb;
+        for (long long jb = nblk - 1; jb >= 0; --jb) {
+            const long long j0 = jb * kNb;
+            const int nb = (int)std::min<long long>(kNb, k - j0);
+            tri(TRI_BACK, Mf.as<double>(), k, X, k, (int)j0, nb, 0, ncols, (int)k);
+            // X[0:j0, :] -= R[0:j0, j0:j0+nb] Y_j
+            if (j0 > 0) gemm(A + j0 * k, 1, k, X + j0, 1, k, X, k, (int)j0, ncols, nb, -1.0, 1.0);
+        }
+    }
+
+    void sample(const double* M, const double* Z, int64_t n, double* R, double* L) {
+        factorize(M);
+        const int nvec = (int)n;
+        W.ensure(8 * (size_t)k * std::max<long long>(nvec, 1));
+        // W = P Z ; W <- R^-1 W ; residuals = P W
+        VecParams P = vp();
+        P.op = VOP_FLIP; P.nvec = nvec; P.in = Z; P.out = W.as<double>();
+        vec_launch(ctx, rws, P);
+        back_solve(W.as<double>(), nvec);
+        P.in = W.as<double>(); P.out = R;
+        vec_launch(ctx, rws, P);
+        if (L) {
+            // L_Sigma = P R^-1 P: X = R^-1 (back substitution on the identity); reversing the flat
+            // column-major array maps (i, j) -> (k-1-i, k-1-j)
+            Rinv.ensure(8 * k * k);
+            tri(TRI_EYE, Rinv.as<double>(), k, nullptr, 0, 0, kNb, 0, 0, (int)k);
+            back_solve(Rinv.as<double>(), (int)k);
+            VecParams Q = vp();
+            Q.op = VOP_FLIP; Q.N = k * k; Q.in = Rinv.as<double>(); Q.out = L;
+            vec_launch(ctx, rws, Q);
+        }
+    }
+};
+
+DenseChol* dense_chol_create(mgvib200_ctx* ctx) {
+    DenseChol* c = new DenseChol();
+    c->ctx = ctx;
+    return c;
+}
+void dense_chol_destroy(DenseChol* c) {
+    if (!c) return;
+    c->release();
+    delete c;
+}
+void dense_chol_identity(DenseChol* c, double* eye, long long k) {
+    c->tri(TRI_EYE, eye, k, nullptr, 0, 0, kNb, 0, 0, (int)k);
+}
+void dense_chol_sample(DenseChol* c, const double* M, long long k, const double* Z, int64_t n, double* R, double* L) {
+    c->k = k;
+    c->have_chol = false;        // M belongs to the caller and may have changed (new linearisation)
+    c->sample(M, Z, n, R, L);
+}
+
+namespace {
+
+struct DenseEngine : Engine {
+    long long m = 0, k = 0;
+    double sigma = 1.0, inv_s2 = 1.0, dd = 0.0, const_term = 0.0;
+    int layout = 0;
+    long long z1_stride = 1;
+    DevBuf J, data, M, h, center, P2, MP, gsum, ws_r, ws_p, ws_t, n_x, n_r, n_p, n_t;
+    DevBuf fvec, sqf;            // per-datum Fisher weight 1/sigma_i^2 and its square root (null: constant sigma)
+    std::vector<double> h_f;     // host copy (get_weights)
+    ReduceWs rws;
+    CgWs cgws, ncgws;
+    CgScalars ncg_sc;
+    bool ncg_first = true;
+    int h_act = 0;
+
+    bool counted = false;
+    // "replicas only" (SURVEY.md 8e): mgvib200_comm_init refuses contexts that hold a dense model, setup()
+    // refuses a context that already has a communicator; this covers every entry point that would sum
+    // over residual samples
+    void single_rank_only() const {
+        if (ctx->world > 1) throw RtError{"DENSE_LINEAR: replicas only (SURVEY.md 8e); run one replica per GPU", 3};
+    }
+
+    ~DenseEngine() override {
+        if (counted) ctx->n_models_single_rank--;
+        DevBuf* all[] = {&J, &data, &M, &h, &center, &P2, &MP, &gsum, &ws_r, &ws_p, &ws_t, &n_x, &n_r, &n_p,
+                         &n_t, &fvec, &sqf, &rws.partials, &rws.counters, &rws.red};
+        for (auto* b : all) b->release();
+        chol.release();
+    }
+
+    DenseChol chol;
+    void gemm(const double* A, long long a_row, long long a_k, const double* B, long long b_k, long long b_col,
+              double* C, long long ldc, int Mr, int Nc, int Kr, double alpha, double beta, bool upper_only = false,
+              const double* kweight = nullptr) {
+        chol.gemm(A, a_row, a_k, B, b_k, b_col, C, ldc, Mr, Nc, Kr, alpha, beta, upper_only, kweight);
+    }
+    void tri(int mode, double* A, long long ld, double* X, long long ldx, int j0, int nb, int c0, int ncols, int n) {
+        chol.tri(mode, A, ld, X, ldx, j0, nb, c0, ncols, n);
+    }
+
+    VecParams vp() const {
+        VecParams P;
+        memset(&P, 0, sizeof P);
+        P.nvec = 1; P.N = k;
+        return P;
+    }
+
     void setup(const mgvib200_model_desc& d) {
         m = d.m; k = d.k; sigma = d.sigma; layout = d.lambda_layout;
         if (d.likelihood != MGVIB200_LIKE_NORMAL) throw RtError{"DENSE_LINEAR: Normal likelihood only", 1};
@@ -228,19 +344,45 @@ struct DenseEngine : Engine {
         n_theta = k;
         n_lambda = (layout == MGVIB200_LAYOUT_MU_ONLY) ? m : 2 * m;
         z1_stride = (layout == MGVIB200_LAYOUT_INTERLEAVED) ? 2 : 1;
+        chol.ctx = ctx;
         J.ensure(8 * m * k); data.ensure(8 * m); M.ensure(8 * k * k); h.ensure(8 * k); center.ensure(8 * k);
         rt_h2d(J.p, d.J, 8 * m * k, ctx->stream);
         rt_h2d(data.p, d.data, 8 * m, ctx->stream);
         dd = 0.0;
-        for (long long i = 0; i < m; ++i) dd += d.data[i] * d.data[i];
-        dd *= inv_s2;
-        const_term = (double)m * (log(sigma) + 0.5 * log(2.0 * M_PI)) + 0.5 * (double)k * log(2.0 * M_PI);
-        // M = I + J'J / sigma^2 : identity, rank-m update of the upper block tiles on DMMA, mirror
+        const double* fw = nullptr;
+        double a_scale = inv_s2;
+        if (d.sigma_vec) {
+            // per-datum noise level: F = diag(1 / sigma_i^2) (src/information.jl:12-18), folded into the
+            // A-operand load of the DMMA rank-m update
+            h_f.resize(m);
+            std::vector<double> hq(m);
+            double logs = 0.0;
+            for (long long i = 0; i < m; ++i) {
+                const double sg = d.sigma_vec[i];
+                if (!(sg > 0)) throw RtError{"DENSE_LINEAR: every sigma_vec entry must be positive", 1};
+                h_f[i] = (1.0 / sg) * (1.0 / sg);
+                hq[i] = 1.0 / sg;
+                dd += h_f[i] * d.data[i] * d.data[i];
+                logs += log(sg);
+            }
+            fvec.ensure(8 * m); sqf.ensure(8 * m);
+            rt_h2d(fvec.p, h_f.data(), 8 * m, ctx->stream);
+            rt_h2d(sqf.p, hq.data(), 8 * m, ctx->stream);
+            rt_sync(ctx->stream);
+            fw = fvec.as<double>();
+            a_scale = 1.0;
+            const_term = logs + (double)m * 0.5 * log(2.0 * M_PI) + 0.5 * (double)k * log(2.0 * M_PI);
+        } else {
+            for (long long i = 0; i < m; ++i) dd += d.data[i] * d.data[i];
+            dd *= inv_s2;
+            const_term = (double)m * (log(sigma) + 0.5 * log(2.0 * M_PI)) + 0.5 * (double)k * log(2.0 * M_PI);
+        }
+        // M = I + J'FJ : identity, rank-m update of the upper block tiles on DMMA, mirror
         tri(TRI_EYE, M.as<double>(), k, nullptr, 0, 0, kNb, 0, 0, (int)k);
-        gemm(J.as<double>(), m, 1, J.as<double>(), 1, m, M.as<double>(), k, (int)k, (int)k, (int)m, inv_s2, 1.0, true);
+        gemm(J.as<double>(), m, 1, J.as<double>(), 1, m, M.as<double>(), k, (int)k, (int)k, (int)m, a_scale, 1.0, true, fw);
         tri(TRI_SYM, M.as<double>(), k, nullptr, 0, 0, kNb, 0, 0, (int)k);
-        // h = J'd / sigma^2
-        gemm(J.as<double>(), m, 1, data.as<double>(), 1, m, h.as<double>(), k, (int)k, 1, (int)m, inv_s2, 0.0);
+        // h = J'F d
+        gemm(J.as<double>(), m, 1, data.as<double>(), 1, m, h.as<double>(), k, (int)k, 1, (int)m, a_scale, 0.0, false, fw);
         rt_sync(ctx->stream);
     }
 
@@ -248,8 +390,8 @@ struct DenseEngine : Engine {
 
     void get_weights(double* w_host, double* q_host) override {
         for (long long i = 0; i < m; ++i) {
-            if (w_host) w_host[i] = inv_s2;
-            if (q_host) q_host[i] = 1.0 / sigma;
+            if (w_host) w_host[i] = h_f.empty() ? inv_s2 : h_f[i];
+            if (q_host) q_host[i] = h_f.empty() ? 1.0 / sigma : sqrt(h_f[i]);
         }
     }
 
@@ -272,7 +414,8 @@ struct DenseEngine : Engine {
         rt_event_record(ctx->ev0, ctx->stream);
         // b = J'(sqrt(F) n1) + eta   (src/residual_samplers.jl:77): t = eta, t += (1/sigma) J' n1_mu
         rt_d2d(ws_t.p, Z2, vb, ctx->stream);
-        gemm(J.as<double>(), m, 1, Z1, z1_stride, n_lambda, ws_t.as<double>(), k, (int)k, nvec, (int)m, 1.0 / sigma, 1.0);
+        gemm(J.as<double>(), m, 1, Z1, z1_stride, n_lambda, ws_t.as<double>(), k, (int)k, nvec, (int)m,
+             sqf.p ? 1.0 : 1.0 / sigma, 1.0, false, sqf.p ? sqf.as<double>() : nullptr);
         vec_cg_init(ctx, rws, sc, ws_t.as<double>(), k, R, ws_r.as<double>(), ws_p.as<double>(), k, nvec);
         int* hp = ctx->h_pinned;
         rt_d2h(hp, cgws.n_active.p, sizeof(int), ctx->stream);
@@ -315,63 +458,10 @@ struct DenseEngine : Engine {
         ctx->lockstep_iters = mx;
     }
 
-    // Mf = P M P = R'R, R upper, blocked right-looking; the factor stays in Mf (upper triangle)
-    void factorize() {
-        if (have_chol) return;
-        Mf.ensure(8 * k * k);
-        // flip rows and columns: Mf[i][j] = M[k-1-i][k-1-j]; with M symmetric a flip of the flat array does it
-        VecParams P = vp();
-        P.op = VOP_FLIP; P.N = k * k; P.in = M.as<double>(); P.out = Mf.as<double>();
-        vec_launch(ctx, rws, P);
-        double* A = Mf.as<double>();
-        for (long long j0 = 0; j0 < k; j0 += kNb) {
-            const int nb = (int)std::min<long long>(kNb, k - j0);
-            tri(TRI_POTRF, A, k, nullptr, 0, (int)j0, nb, 0, 0, (int)k);
-            const int rest = (int)(k - j0 - nb);
-            if (rest > 0) {
-                tri(TRI_PANEL, A, k, A, k, (int)j0, nb, (int)(j0 + nb), rest, (int)k);
-                // trailing update A22 -= X'X, X = A[j0:j0+nb, j0+nb:]  (upper block tiles only)
-                const double* X = A + j0 + (j0 + nb) * k;
-                gemm(X, k, 1, X, 1, k, A + (j0 + nb) + (j0 + nb) * k, k, rest, rest, nb, -1.0, 1.0, true);
-            }
-        }
-        have_chol = true;
-    }
-
-    // X (k x ncols, leading dimension k) <- R^-1 X, blocked back substitution
-    void back_solve(double* X, int ncols) {
-        const double* A = Mf.as<double>();
-        const long long nblk = (k + kNb - 1) / kNb;
-        for (long long jb = nblk - 1; jb >= 0; --jb) {
-            const long long j0 = jb * kNb;
-            const int nb = (int)std::min<long long>(kNb, k - j0);
-            tri(TRI_BACK, Mf.as<double>(), k, X, k, (int)j0, nb, 0, ncols, (int)k);
-            // X[0:j0, :] -= R[0:j0, j0:j0+nb] Y_j
-            if (j0 > 0) gemm(A + j0 * k, 1, k, X + j0, 1, k, X, k, (int)j0, ncols, nb, -1.0, 1.0);
-        }
-    }
-
     void sample_dense(const double* Z, int64_t n, double* R, double* L) override {
-        factorize();
-        const int nvec = (int)n;
-        W.ensure(8 * (size_t)k * std::max<long long>(nvec, 1));
-        // W = P Z ; W <- R^-1 W ; residuals = P W
-        VecParams P = vp();
-        P.op = VOP_FLIP; P.nvec = nvec; P.in = Z; P.out = W.as<double>();
-        vec_launch(ctx, rws, P);
-        back_solve(W.as<double>(), nvec);
-        P.in = W.as<double>(); P.out = R;
-        vec_launch(ctx, rws, P);
-        if (L) {
-            // L_Sigma = P R^-1 P: X = R^-1 (back substitution on the identity); reversing the flat
-            // column-major array maps (i, j) -> (k-1-i, k-1-j)
-            Rinv.ensure(8 * k * k);
-            tri(TRI_EYE, Rinv.as<double>(), k, nullptr, 0, 0, kNb, 0, 0, (int)k);
-            back_solve(Rinv.as<double>(), (int)k);
-            VecParams Q = vp();
-            Q.op = VOP_FLIP; Q.N = k * k; Q.in = Rinv.as<double>(); Q.out = L;
-            vec_launch(ctx, rws, Q);
-        }
+        // M is fixed at model creation, so the factor is kept across calls
+        chol.k = k;
+        chol.sample(M.as<double>(), Z, n, R, L);
     }
 
     double kl_value_grad(const double* x, const double* R, int64_t n, double* grad) override {

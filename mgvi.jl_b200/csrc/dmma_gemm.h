@@ -24,6 +24,8 @@ struct GemmParams {
     double alpha, beta;
     int upper_only;     // compute only block tiles with tile_col >= tile_row
     int ntm, ntn;
+    const double* kweight;   // optional diagonal weight along the reduction index, folded into the A-operand
+                             // load: C = alpha * op(A) diag(kweight) op(B) + beta C  (the Fisher diagonal of J'FJ)
 };
 
 static const int kGemmBM = 128, kGemmBN = 128, kGemmBK = 16, kGemmLd = 20;   // row stride 20 doubles: 2-way at most
@@ -50,7 +52,7 @@ SIMT_DEVICE void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
 // Each thread fetches 8 doubles: kcontig: (row = t/8 + 32 r, k = 2 (t%8) + {0,1}), r = 0..3
 //                                 else   : (row = 2 (t%64) + {0,1}, k = t/64 + 4 r),   r = 0..3
 SIMT_DEVICE void gemm_fetch(double (&reg)[8], const double* __restrict__ X, long long s_row, long long s_k, int row0,
-                            int k0, int nrow, int nk, bool kcontig) {
+                            int k0, int nrow, int nk, bool kcontig, const double* __restrict__ kweight = nullptr) {
     const int t = SIMT_TID;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -60,7 +62,9 @@ SIMT_DEVICE void gemm_fetch(double (&reg)[8], const double* __restrict__ X, long
             if (kcontig) { row = (t >> 3) + 32 * r; k = 2 * (t & 7) + e; }
             else { row = 2 * (t & 63) + e; k = (t >> 6) + 4 * r; }
             const bool ok = (row0 + row < nrow) && (k0 + k < nk);
-            reg[2 * r + e] = ok ? X[(long long)(row0 + row) * s_row + (long long)(k0 + k) * s_k] : 0.0;
+            double xv = ok ? X[(long long)(row0 + row) * s_row + (long long)(k0 + k) * s_k] : 0.0;
+            if (kweight && ok) xv *= SIMT_LDG(kweight + k0 + k);
+            reg[2 * r + e] = xv;
         }
     }
 }
@@ -96,14 +100,14 @@ SIMT_DEVICE void gemm_body(const GemmParams& P, unsigned char* smem) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
     double ra[8], rb[8];
-    gemm_fetch(ra, P.A, P.a_row, P.a_k, row0, 0, P.M, P.K, a_kc);
+    gemm_fetch(ra, P.A, P.a_row, P.a_k, row0, 0, P.M, P.K, a_kc, P.kweight);
     gemm_fetch(rb, P.B, P.b_col, P.b_k, col0, 0, P.N, P.K, b_kc);
     for (int k0 = 0; k0 < P.K; k0 += kGemmBK) {
         gemm_stash(ra, As, a_kc);
         gemm_stash(rb, Bs, b_kc);
         SIMT_SYNC();
         if (k0 + kGemmBK < P.K) {
-            gemm_fetch(ra, P.A, P.a_row, P.a_k, row0, k0 + kGemmBK, P.M, P.K, a_kc);
+            gemm_fetch(ra, P.A, P.a_row, P.a_k, row0, k0 + kGemmBK, P.M, P.K, a_kc, P.kweight);
             gemm_fetch(rb, P.B, P.b_col, P.b_k, col0, k0 + kGemmBK, P.N, P.K, b_kc);
         }
 #pragma unroll

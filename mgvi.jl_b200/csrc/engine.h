@@ -134,6 +134,16 @@ struct Engine {
 Engine* make_field_engine(mgvib200_ctx* ctx, const mgvib200_model_desc& d);
 Engine* make_poly_engine(mgvib200_ctx* ctx, const mgvib200_model_desc& d);
 Engine* make_dense_engine(mgvib200_ctx* ctx, const mgvib200_model_desc& d);
+Engine* make_hyper_engine(mgvib200_ctx* ctx, const mgvib200_model_desc& d);
+
+// MatrixInversion sampler (src/residual_samplers.jl:95-123) on a materialised symmetric metric M (k x k,
+// device memory; dense_engine.cu): blocked Cholesky of the index-reversed M on the FP64 tensor pipe,
+// residuals R = L_Sigma Z and optionally L_Sigma itself.  Used by the field engines for small models.
+struct DenseChol;
+DenseChol* dense_chol_create(mgvib200_ctx* ctx);
+void dense_chol_destroy(DenseChol* c);
+void dense_chol_identity(DenseChol* c, double* eye, long long k);      // eye = I_k
+void dense_chol_sample(DenseChol* c, const double* M, long long k, const double* Z, int64_t n, double* R, double* L);
 
 // communicator (comm.cu)
 void comm_allgather(mgvib200_ctx* ctx, const double* send_dev, double* recv_dev, long long count_per_rank);

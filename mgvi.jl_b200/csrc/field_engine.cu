@@ -21,6 +21,7 @@ namespace {
 #endif
 const int kNaiveMaxAxis = 4096;
 const long long kFastMaxAxis = 4096;
+const long long kDenseFieldMax = 8192;
 
 bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
 int ilog2(long long v) { int l = 0; while ((1LL << l) < v) ++l; return l; }
@@ -64,6 +65,8 @@ struct FieldEngine : Engine {
     DevBuf qsum;                      // N
     DevBuf n_x, n_r, n_p, n_t;        // Newton CG state (single vector)
     DevBuf tmpA, tmpB;                // generic-path staging [nvec][N]
+    DevBuf Mdense, eye;               // MatrixInversion sampler: materialised metric (small fields only)
+    DenseChol* chol = nullptr;
     // replayable chunk of the sampler's lock-step CG iterations (sample_cg)
     struct CgGraphKey {
         const void *R, *r, *p, *t, *tile, *wt;
@@ -87,6 +90,8 @@ struct FieldEngine : Engine {
 
     ~FieldEngine() override {
         if (cg_graph_valid) rt_graph_destroy(cg_graph);
+        dense_chol_destroy(chol);
+        Mdense.release(); eye.release();
         DevBuf* all[] = {&A, &data, &w, &q, &wbar, &center, &w_tiled, &ws_tile, &ws_r, &ws_p, &ws_t, &pt_t, &gather, &sc_gather, &kl_red, &qsum, &n_x, &n_r,
                          &n_p, &n_t, &tmpA, &tmpB, &rws.partials, &rws.counters, &rws.red};
         for (auto* b : all) b->release();
@@ -776,8 +781,22 @@ struct FieldEngine : Engine {
         ctx->lockstep_iters = mx;
     }
 
-    void sample_dense(const double*, int64_t, double*, double*) override {
-        throw RtError{"FIELD_DHT: the MatrixInversion sampler is only provided for POLY and DENSE_LINEAR models", 3};
+    // MatrixInversion (src/residual_samplers.jl:95-123): the reference materialises M = J'FJ + I by n_theta
+    // operator applications (:102-104) -- here one batched metric product on the identity -- then the
+    // shared Cholesky sampler (dense_engine.cu).  Meant for small fields (the dense-vs-CG Bartlett check of
+    // test/test_samplers.jl:17-39); the matrix is n_theta^2 doubles.
+    void sample_dense(const double* Z, int64_t n, double* R, double* L) override {
+        if (N > kDenseFieldMax)
+            throw RtError{"FIELD_DHT: the MatrixInversion sampler materialises the n_theta x n_theta metric; provided for fields of up to 8192 pixels", 3};
+        Mdense.ensure(sizeof(double) * N * N);
+        eye.ensure(sizeof(double) * N * N);
+        if (!chol) chol = dense_chol_create(ctx);
+        dense_chol_identity(chol, eye.as<double>(), N);
+        for (long long c0 = 0; c0 < N; c0 += 1024) {           // bounded scratch: 1024 columns per batch
+            const long long nc = std::min<long long>(1024, N - c0);
+            metric_apply(eye.as<double>() + c0 * N, nc, Mdense.as<double>() + c0 * N);
+        }
+        dense_chol_sample(chol, Mdense.as<double>(), N, Z, n, R, L);
     }
 
     double kl_value_grad(const double* x, const double* R, int64_t n, double* grad) override {

@@ -381,7 +381,7 @@ class PolyModel:
 
 
 class DenseLinearModel:
-    """mu = Jm @ xi, Normal(mu, sigma) with constant sigma -- BASELINE.json configs[3]; the
+    """mu = Jm @ xi, Normal(mu, sigma) with constant or per-datum sigma -- BASELINE.json configs[3]; the
     operator type `DenseMatrix` that `_get_operator_type(::MatrixInversion)` selects
     (src/residual_samplers.jl:56)."""
 
@@ -389,24 +389,27 @@ class DenseLinearModel:
         self.Jm = np.asarray(Jm, dtype=np.float64)
         self.m, self.k = self.Jm.shape
         self.N = self.m
-        self.sigma = float(sigma)
+        self.sigma = float(sigma) if np.ndim(sigma) == 0 else np.asarray(sigma, dtype=np.float64).reshape(self.m)
         self.data = np.asarray(data, dtype=np.float64).reshape(self.m)
         self.layout = int(layout)
         self.mu_idx, self.n_lambda = _mu_index(self.m, self.layout)
         self.noise_idx = _noise_index(self.m, self.layout)
         self.n_theta = self.k
+        self.log_sigma_sum = float(np.sum(np.log(np.broadcast_to(self.sigma, (self.m,)))))
 
     def lam(self, xi):
         out = np.empty(self.n_lambda)
         out[self.mu_idx] = self.Jm @ xi
-        out[self.noise_idx] = self.sigma if self.layout == LAYOUT_INTERLEAVED else self.sigma ** 2
+        if self.noise_idx.size:
+            out[self.noise_idx] = self.sigma if self.layout == LAYOUT_INTERLEAVED else self.sigma ** 2
         return out
 
     def linearize(self, xi) -> Linearization:
         inv_s = 1.0 / self.sigma
         F = np.empty(self.n_lambda)
         F[self.mu_idx] = inv_s * inv_s
-        F[self.noise_idx] = 2.0 * (inv_s * inv_s)
+        if self.noise_idx.size:
+            F[self.noise_idx] = 2.0 * (inv_s * inv_s)
         mu_idx, n_lambda = self.mu_idx, self.n_lambda
 
         def jvp(v):
@@ -423,7 +426,7 @@ class DenseLinearModel:
 
     def loglike(self, xi):
         z = (self.data - self.Jm @ xi) / self.sigma
-        return float(np.sum(-0.5 * z * z) - self.m * (math.log(self.sigma) + 0.5 * LOG2PI))
+        return float(np.sum(-0.5 * z * z) - self.log_sigma_sum - self.m * 0.5 * LOG2PI)
 
     def grad_loglike(self, xi):
         return self.Jm.T @ ((self.data - self.Jm @ xi) / (self.sigma * self.sigma))

@@ -425,3 +425,91 @@ def test_lbfgs_optimizer_seam(pkg, emu_ctx):
     assert rel(res.samples, O.build_samples(Ro, center)) < RTOL
     assert res.info["optimizer_output"].nit >= 1
     m.close()
+
+
+def _small_hyper_cfg(pkg, n_data=10, grain=2, n=2, start_scale=0.3):
+    """A small instance of the tutorial's model (docs/src/advanced_tutorial_lit.jl): `produce_bins` on a
+    10-bin histogram with padding, two hyperparameters in front of the latent field."""
+    counts = np.random.default_rng(3).poisson(4.0, n_data)
+    return pkg.synthetic.hyper_field_config(counts, n, grain=grain, padding=4.0, xlim=(0.0, 10.0),
+                                            start_scale=start_scale)
+
+
+@pytest.mark.parametrize("grain", [1, 2, 3])
+def test_hyper_field_model_vs_oracle(pkg, emu_ctx, grain):
+    """amplitude-spectrum hyperparameters (two extra Jacobian columns) + bin aggregation
+    (`agg_lambdas`) + Poisson counts -- every row of the path against the oracle, then a full mgvi_step."""
+    # (grain 3 triples the kernel amplitude a0 = 2 grain: a start closer to the prior mean keeps exp() finite in
+    # the first line search -- beyond that the reference itself returns NaN)
+    cfg = _small_hyper_cfg(pkg, grain=grain, start_scale=0.3 if grain < 3 else 0.1)
+    out = check_field_ops(pkg, emu_ctx, cfg, check_step=True)
+    assert_field_ops(out, cfg)
+    # Fisher weights in lambda space: 1 / Lambda_b (src/information.jl:74-78)
+    m = pkg.model_from_config(cfg, emu_ctx)
+    om = oracle_model(cfg)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(**TIGHT), emu_ctx)
+    w, q = s.weights()
+    lam = om.lam(cfg["center"])
+    assert rel(w, 1.0 / lam) < RTOL and rel(q, np.sqrt(1.0 / lam)) < RTOL
+    m.close()
+
+
+def test_hyper_field_jacobian_consistency(pkg, emu_ctx):
+    """test/test_jacobians.jl:28-32,45-49 on the tutorial model: J v against central differences of the
+    forward model, and <J v, l> = <v, J' l>; the device metric against the dense J'FJ + I."""
+    cfg = _small_hyper_cfg(pkg)
+    om = oracle_model(cfg)
+    c = cfg["center"]
+    lin = om.linearize(c)
+    rng = np.random.default_rng(0)
+    v, l = rng.standard_normal(om.n_theta), rng.standard_normal(om.n_lambda)
+    h = 1e-6
+    fd = (om.lam(c + h * v) - om.lam(c - h * v)) / (2 * h)
+    assert rel(lin.jvp(v), fd) < 1e-5                          # the reference's own tolerance
+    assert abs(lin.jvp(v) @ l - v @ lin.vjp(l)) < 1e-10 * abs(lin.jvp(v) @ l)
+    J = lin.dense()
+    Md = J.T @ (lin.fisher[:, None] * J) + np.eye(om.n_theta)
+    m = pkg.model_from_config(cfg, emu_ctx)
+    s = pkg.ResidualSampler(m, c, pkg.B200CG(), emu_ctx)
+    assert rel(s.metric_apply(np.eye(om.n_theta)), Md) < RTOL
+    m.close()
+
+
+@pytest.mark.parametrize("kind", ["field1d", "field2d", "field_generic", "hyper"])
+def test_matrix_inversion_sampler_on_field_models(pkg, emu_ctx, kind):
+    """src/residual_samplers.jl:95-123 on the field families (the dense-vs-CG comparison of
+    test/test_samplers.jl:17-39 needs it): L_Sigma and R = L_Sigma Z against the oracle's dense sampler,
+    and L_Sigma L_Sigma' = inv(M) against the device's own metric."""
+    syn = pkg.synthetic
+    cfg = {"field1d": lambda: syn.field_config((32,), syn.LIKE_POISSON, 3, field_std=0.5),
+           "field2d": lambda: syn.field_config((8, 16), syn.LIKE_NORMAL, 3, field_std=0.5, layout=1),
+           "field_generic": lambda: syn.field_config((6, 10), syn.LIKE_POISSON, 3, field_std=0.5),
+           "hyper": lambda: _small_hyper_cfg(pkg, n=3)}[kind]()
+    m = pkg.model_from_config(cfg, emu_ctx)
+    om = oracle_model(cfg)
+    c = cfg["center"]
+    Z = np.random.default_rng(42).standard_normal((m.n_theta, 3))
+    s = pkg.ResidualSampler(m, c, pkg.MatrixInversion(), emu_ctx)
+    R = pkg.sample_residuals(s, 3, draws=Z)
+    Ro, Lo = O.sample_residuals_dense(om, c, Z)
+    assert rel(R, Ro) < RTOL
+    Zf = np.asfortranarray(Z)
+    R2 = np.empty((m.n_theta, 3), order="F")
+    L = np.empty((m.n_theta, m.n_theta), order="F")
+    emu_ctx.check(emu_ctx.lib.sample_residuals_dense(m.handle, pkg.capi.ptr(Zf), 3, pkg.capi.ptr(R2), pkg.capi.ptr(L)))
+    assert rel(L, Lo) < RTOL and np.array_equal(R2, R)
+    M = s.metric_apply(np.eye(m.n_theta))
+    assert rel(L @ L.T @ M, np.eye(m.n_theta)) < 1e-9
+    m.close()
+
+
+def test_dense_linear_per_datum_sigma(pkg, emu_ctx):
+    """Diagonal Fisher with one sigma per datum folded into the A-operand load of the DMMA J'FJ GEMM
+    (BASELINE north_star d)."""
+    from helpers import check_dense_ops
+    cfg = pkg.synthetic.dense_linear_config(70, 24, 3)
+    cfg["sigma"] = 0.3 + np.random.default_rng(9).random(70)
+    cfg["data"] = cfg["J"] @ np.random.default_rng(128).standard_normal(24) + cfg["sigma"] * np.random.default_rng(7).standard_normal(70)
+    out = check_dense_ops(pkg, emu_ctx, cfg)
+    for k in ("metric", "residuals", "dense", "L", "kl", "grad", "mean_metric", "dense_step_residuals"):
+        assert out[k] < RTOL, (k, out)

@@ -10,7 +10,7 @@ import pytest
 
 import oracle as O
 from golden_io import load_golden
-from helpers import RTOL, TIGHT, assert_field_ops, check_field_ops, oracle_model, rel
+from helpers import RTOL, TIGHT, TIGHT_O, assert_field_ops, check_field_ops, oracle_model, rel
 
 pytestmark = pytest.mark.gpu
 
@@ -332,3 +332,169 @@ def test_dense_block_edges(pkg, gpu_ctx, m, k, n):
     for key in ("metric", "residuals", "dense", "L", "kl", "grad", "mean_metric"):
         assert out[key] < 1e-10, (key, out)
     assert out["L_lower"] == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# the tutorial's model (amplitude-spectrum hyperparameters + bin aggregation) and the
+# coal-mining run of docs/src/advanced_tutorial_lit.jl:489-556
+# ------------------------------------------------------------------------------------------------
+def _coal_cfg(pkg, n=3, start_scale=1.0):
+    from golden_io import GOLDEN
+    import os
+    counts = np.load(os.path.join(GOLDEN, "coal_mining_counts.npz"))["counts"]
+    return pkg.synthetic.hyper_field_config(counts, n, start_scale=start_scale)
+
+
+def test_hyper_field_every_row_at_tutorial_size(pkg, gpu_ctx):
+    """The tutorial's grid (110 yearly bins, GP_GRAIN_FACTOR 3, padding 80: ~800 fine pixels + 2
+    hyperparameters), 3 residuals: metric product, CG residuals, KL value / gradient, mean metric (n
+    per-sample metrics, canonical sum), sample assembly and one full mgvi_step against the oracle."""
+    cfg = _coal_cfg(pkg, start_scale=0.3)
+    assert_field_ops(check_field_ops(pkg, gpu_ctx, cfg, check_step=True), cfg)
+
+
+def test_coal_mining_tutorial_run(pkg, gpu_ctx):
+    """docs/src/advanced_tutorial_lit.jl:489-556: first iteration with KrylovJL_CG(itmax = 10) and
+    NewtonCG(steps = 1), then iterations with KrylovJL_CG(atol = 1e-2) and the default NewtonCG, 3
+    residuals each, every iteration fed the previous centre.  The chain is compared ITERATION BY
+    ITERATION: the device's mgvi_step starts from the oracle's centre of that iteration with the same
+    draws (teacher forcing: end-to-end chains of truncated Newton steps amplify rounding), and a
+    free-running device chain must reproduce the tutorial's convergence."""
+    from helpers import assert_step_parity
+    cfg = _coal_cfg(pkg, start_scale=1.0)
+    m = pkg.model_from_config(cfg, gpu_ctx)
+    om = oracle_model(cfg)
+    n, nt, nl = 3, cfg["n_theta"], cfg["n_lambda"]
+    rng = np.random.default_rng(2024)
+
+    def draws():
+        return rng.standard_normal((nl, n)), rng.standard_normal((nt, n))
+
+    def avg_nlp(samples):                                # compute_avg_likelihood (:533-539)
+        return float(np.mean([-O.posterior_loglike(om, samples[:, j]) for j in range(samples.shape[1])]))
+
+    c_or = cfg["center"].copy()
+    c_dev = cfg["center"].copy()
+    series_or, series_dev = [], []
+    stages = [(dict(maxiters=10), dict(steps=1), dict(itmax=10))] + \
+             [(dict(abstol=1e-2), dict(), dict(atol=1e-2))] * 8
+    for it, (cg_kw, ncg_kw, ocg_kw) in enumerate(stages):
+        Z1, Z2 = draws()
+        conf = pkg.MGVIConfig(linsolver=pkg.B200CG(**cg_kw), optimizer=pkg.NewtonCG(**ncg_kw))
+        ref = O.mgvi_step(om, c_or, Z1=Z1, Z2=Z2, opts=O.NewtonCGOpts(**ncg_kw), **ocg_kw)
+        # The tutorial stops the sampler CG early (itmax = 10 / atol = 1e-2).  The k-th iterate of a truncated CG
+        # is an ill-conditioned function of its inputs (measured on this very start: one-ulp input perturbations
+        # move the ORACLE's 10th iterate by 1e-5, its 4th by 3e-15), so the residual tolerance is the oracle's
+        # own measured reproducibility of exactly this solve, x 100 -- and never below 1e-10.
+        sens = 0.0
+        for sd in range(2):
+            pr = np.random.default_rng(500 + sd)
+            Rp, itp, _ = O.sample_residuals_cg(om, c_or * (1 + np.finfo(float).eps * pr.standard_normal(nt)), Z1,
+                                               Z2 * (1 + np.finfo(float).eps * pr.standard_normal(Z2.shape)), **ocg_kw)
+            sens = max(sens, rel(Rp, ref["residuals"]))
+        rtol_R = max(RTOL, 100.0 * sens)
+        assert rtol_R < 1e-2, (it, sens)
+        # teacher-forced: the device's step from the oracle's centre
+        res, cn = pkg.mgvi_step(m, cfg["data"], n, c_or, conf, gpu_ctx, draws=(Z1, Z2))
+        assert res.info["linsolver_output"]["iters"].tolist() == ref["sampler_iters"].tolist(), it
+        step_cfg = dict(cfg, center=c_or)
+        assert_step_parity(pkg, m, om, step_cfg, res, cn, ref, label="coal mining it %d" % it, opts_kw=ncg_kw,
+                           residual_tol=rtol_R)
+        # the solve itself, where it is well-conditioned: the first 4 CG iterations at 1e-10
+        s4 = pkg.ResidualSampler(m, c_or, pkg.B200CG(maxiters=4), gpu_ctx)
+        R4 = pkg.sample_residuals(s4, n, draws=(Z1, Z2))
+        R4o, _, _ = O.sample_residuals_cg(om, c_or, Z1, Z2, itmax=4)
+        assert rel(R4, R4o) < RTOL, (it, rel(R4, R4o))
+        series_or.append(avg_nlp(ref["samples"]))
+        # free-running device chain
+        res_d, c_dev = pkg.mgvi_step(m, cfg["data"], n, c_dev, conf, gpu_ctx, draws=(Z1, Z2))
+        series_dev.append(avg_nlp(res_d.samples))
+        c_or = ref["center"]
+    # the tutorial's observation: the average -log posterior of the samples falls steeply and flattens
+    assert series_dev[-1] < series_dev[0] and series_or[-1] < series_or[0]
+    assert abs(series_dev[-1] - series_or[-1]) < 0.05 * abs(series_or[-1]), (series_dev, series_or)
+    # posterior mean rate is positive and of the order of the observed counts
+    lam = om.lam(c_dev)
+    assert np.all(lam > 0) and 0.2 < lam.sum() / cfg["data"].sum() < 5.0
+    m.close()
+
+
+@pytest.mark.parametrize("kind", ["field1d", "field2d", "hyper"])
+def test_matrix_inversion_on_field_models_and_bartlett(pkg, gpu_ctx, kind):
+    """src/residual_samplers.jl:95-123 on the field families, and the reference's own sampler test
+    (test/test_samplers.jl:17-39) on them: L_Sigma against the oracle (LAPACK); the empirical covariance
+    of many CG residual samples against Sigma = L_Sigma L_Sigma' within the reference's factor-of-10
+    element tolerance and far tighter in the trace."""
+    syn = pkg.synthetic
+    cfg = {"field1d": lambda: syn.field_config((256,), syn.LIKE_POISSON, 4, field_std=0.5),
+           "field2d": lambda: syn.field_config((16, 32), syn.LIKE_NORMAL, 4, field_std=0.5, layout=1),
+           "hyper": lambda: _coal_cfg(pkg, 4, start_scale=0.3)}[kind]()
+    m = pkg.model_from_config(cfg, gpu_ctx)
+    om = oracle_model(cfg)
+    c, nt, nl = cfg["center"], cfg["n_theta"], cfg["n_lambda"]
+    Z = np.asfortranarray(np.random.default_rng(42).standard_normal((nt, 4)))
+    sd = pkg.ResidualSampler(m, c, pkg.MatrixInversion(), gpu_ctx)
+    R = np.empty((nt, 4), order="F")
+    L = np.empty((nt, nt), order="F")
+    gpu_ctx.check(gpu_ctx.lib.sample_residuals_dense(m.handle, pkg.capi.ptr(Z), 4, pkg.capi.ptr(R), pkg.capi.ptr(L)))
+    Ro, Lo = O.sample_residuals_dense(om, c, Z)
+    assert rel(R, Ro) < RTOL and rel(L, Lo) < RTOL
+    assert np.abs(np.triu(L, 1)).max() == 0.0
+    # Bartlett-style comparison: covariance of n_s CG samples vs Sigma
+    ns = 4000
+    rng = np.random.default_rng(7)
+    sc = pkg.ResidualSampler(m, c, pkg.B200CG(), gpu_ctx)
+    Rcg = pkg.sample_residuals(sc, ns, draws=(rng.standard_normal((nl, ns)), rng.standard_normal((nt, ns))))
+    Sig = L @ L.T
+    emp = Rcg @ Rcg.T / ns
+    d_emp, d_sig = np.diag(emp), np.diag(Sig)
+    assert np.all(d_emp < 10 * d_sig) and np.all(d_sig < 10 * d_emp)           # test_samplers.jl:31,37-38
+    assert abs(np.trace(emp) - np.trace(Sig)) < 0.05 * np.trace(Sig)
+    # whitened samples have unit covariance: mean squared norm of L^-1 r = n_theta
+    import scipy.linalg
+    wn = scipy.linalg.solve_triangular(L, Rcg, lower=True)
+    assert abs(np.mean(np.sum(wn * wn, axis=0)) / nt - 1.0) < 0.02
+    m.close()
+
+
+def test_dense_linear_per_datum_sigma(pkg, gpu_ctx):
+    """Per-datum Fisher weights folded into the A-operand load of the DMMA J'FJ GEMM, at a size that
+    crosses GEMM tile and Cholesky block edges."""
+    from helpers import check_dense_ops
+    mm, k, n = 1500, 333, 5
+    cfg = pkg.synthetic.dense_linear_config(mm, k, n)
+    cfg["sigma"] = 0.3 + np.random.default_rng(9).random(mm)
+    cfg["data"] = cfg["J"] @ np.random.default_rng(128).standard_normal(k) + cfg["sigma"] * np.random.default_rng(7).standard_normal(mm)
+    out = check_dense_ops(pkg, gpu_ctx, cfg)
+    for key in ("metric", "residuals", "dense", "L", "kl", "grad", "mean_metric", "dense_step_residuals"):
+        assert out[key] < RTOL, (key, out)
+
+
+def test_mgvi_sample_and_pushfwd_on_gpu(pkg, gpu_ctx):
+    """`mgvi_sample` (src/mgvi_impl.jl:166-174: samples around a fixed centre, no
+    optimisation) and `mgvi_mvnormal_pushfwd_function` (:191-198) on the product library."""
+    syn = pkg.synthetic
+    cfg = syn.field_config((32, 64), syn.LIKE_POISSON, 4, field_std=0.5)
+    m = pkg.model_from_config(cfg, gpu_ctx)
+    om = oracle_model(cfg)
+    c = cfg["center"]
+    conf = pkg.MGVIConfig(linsolver=pkg.B200CG(**TIGHT))
+    S = pkg.mgvi_sample(m, cfg["data"], 4, c, conf, gpu_ctx, draws=(cfg["Z1"], cfg["Z2"]))
+    Ro, _, _ = O.sample_residuals_cg(om, c, cfg["Z1"], cfg["Z2"], **TIGHT_O)
+    assert S.shape == (m.n_theta, 8) and rel(S, O.build_samples(Ro, c)) < RTOL
+    assert np.abs(S[:, 0::2] + S[:, 1::2] - 2 * c[:, None]).max() < 1e-12          # antithetic pairs around the GIVEN centre
+    # ... and with the MatrixInversion sampler on a field model
+    Zd = np.random.default_rng(11).standard_normal((m.n_theta, 4))
+    Sd = pkg.mgvi_sample(m, cfg["data"], 4, c, pkg.MGVIConfig(linsolver=pkg.MatrixInversion()), gpu_ctx, draws=Zd)
+    Rd, _ = O.sample_residuals_dense(om, c, Zd)
+    assert rel(Sd, O.build_samples(Rd, c)) < RTOL
+    # push-forward: x -> centre + L_Sigma x on a small field (dense operator)
+    scfg = syn.field_config((64,), syn.LIKE_POISSON, 2, field_std=0.5)
+    sm = pkg.model_from_config(scfg, gpu_ctx)
+    som = oracle_model(scfg)
+    f = pkg.mgvi_mvnormal_pushfwd_function(sm, scfg["data"], pkg.MGVIConfig(), scfg["center"], gpu_ctx)
+    X = np.random.default_rng(3).standard_normal((64, 5))
+    _, Lo = O.sample_residuals_dense(som, scfg["center"], X)
+    Y = np.stack([f(X[:, j]) for j in range(5)], axis=1)
+    assert rel(Y, scfg["center"][:, None] + Lo @ X) < RTOL
+    m.close(); sm.close()
