@@ -69,11 +69,15 @@ def parse():
     ap.add_argument("--ref-samples", type=int, default=0, help="CPU arm: residuals per step; 0 = one per host core")
     ap.add_argument("--ref-iters", type=int, default=2)
     ap.add_argument("--no-configs", action="store_true", help="skip the short C1/C2/C4/C5 measurements")
+    ap.add_argument("--n-residuals", type=int, default=0,
+                    help="override the workload's residual count (tuning: 4 on one GPU is the per-GPU share of C3 on 8 GPUs)")
     return ap.parse_args()
 
 
 def make_config(args, syn):
     dims, like, n = WORKLOADS[args.workload]
+    if getattr(args, "n_residuals", 0) > 0:
+        n = args.n_residuals
     cfg = syn.field_config(dims, getattr(syn, like), n, field_std=args.field_std, draws=False)
     return cfg
 

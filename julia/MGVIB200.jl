@@ -16,7 +16,7 @@ using Random
 import HeterogeneousComputing: GenContext
 import LinearAlgebra
 
-export CorrelatedFieldModel, PolynomialModel, DenseLinearModel
+export CorrelatedFieldModel, PolynomialModel, DenseLinearModel, HyperFieldModel
 export B200CG, B200Dense, B200NewtonCG
 export ImplicitResidualSampler, FullResidualSampler, FwdRevADJacobianFunc, FwdDerJacobianFunc, FullJacobianFunc
 export mgvi_kl_optimize_step
@@ -46,7 +46,14 @@ struct ModelDesc
     J::Ptr{Float64}
     m::Int64
     k::Int64
+    sigma_vec::Ptr{Float64}
+    kdist::Ptr{Float64}
+    hyper::NTuple{4,Float64}
+    bin_start::Int64
+    grain::Int32
+    binsize::Float64
 end
+const _NOHYPER = (C_NULL, (0.0, 0.0, 0.0, 0.0), Int64(0), Int32(0), 0.0)      # kdist, hyper, bin_start, grain, binsize
 
 struct CGOpts
     abstol::Float64
@@ -76,7 +83,7 @@ mutable struct NewtonCGTrace
     NewtonCGTrace() = new()
 end
 
-const MODEL_FIELD_DHT, MODEL_POLY, MODEL_DENSE_LINEAR = Int32(0), Int32(1), Int32(2)
+const MODEL_FIELD_DHT, MODEL_POLY, MODEL_DENSE_LINEAR, MODEL_FIELD_HYPER = Int32(0), Int32(1), Int32(2), Int32(3)
 const LINK_IDENTITY, LINK_EXP = Int32(0), Int32(1)
 const LIKE_NORMAL, LIKE_POISSON = Int32(0), Int32(1)
 const LAYOUT_MU_ONLY, LAYOUT_BLOCKED, LAYOUT_INTERLEAVED = Int32(0), Int32(1), Int32(2)
@@ -141,7 +148,8 @@ function CorrelatedFieldModel(amplitude::Array{Float64,N}, scale::Real, data::Ar
     lay = Dict(:mu_only => LAYOUT_MU_ONLY, :blocked => LAYOUT_BLOCKED, :interleaved => LAYOUT_INTERLEAVED)[layout]
     desc = ModelDesc(MODEL_FIELD_DHT, Int32(N), dims3, pointer(amplitude), scale, offset,
                      link === :exp ? LINK_EXP : LINK_IDENTITY, likelihood === :poisson ? LIKE_POISSON : LIKE_NORMAL,
-                     sigma, lay, pointer(d), length(d), Int32(0), C_NULL, C_NULL, Int32(0), C_NULL, 0.0, C_NULL, 0, 0)
+                     sigma, lay, pointer(d), length(d), Int32(0), C_NULL, C_NULL, Int32(0), C_NULL, 0.0, C_NULL, 0, 0,
+                     C_NULL, _NOHYPER...)
     CorrelatedFieldModel{N}(_create(ctx, desc, amplitude, d), size(amplitude))
 end
 
@@ -162,7 +170,7 @@ function PolynomialModel(x_groups::Vector{Vector{Float64}}, data::Vector{Float64
     lay = layout === :blocked ? LAYOUT_BLOCKED : LAYOUT_INTERLEAVED
     desc = ModelDesc(MODEL_POLY, Int32(0), (0, 0, 0), C_NULL, 0.0, 0.0, Int32(0), LIKE_NORMAL, 0.0, lay, pointer(data),
                      length(data), Int32(length(sizes)), pointer(sizes), pointer(x), Int32(length(cs)), pointer(cs),
-                     noise_scale, C_NULL, 0, 0)
+                     noise_scale, C_NULL, 0, 0, C_NULL, _NOHYPER...)
     PolynomialModel(_create(ctx, desc, x, sizes, cs, data))
 end
 
@@ -175,11 +183,39 @@ struct DenseLinearModel <: B200Model
     handle::ModelHandle
 end
 
-function DenseLinearModel(J::Matrix{Float64}, data::Vector{Float64}; sigma::Real=0.5, ctx::B200Context=b200_context())
-    desc = ModelDesc(MODEL_DENSE_LINEAR, Int32(0), (0, 0, 0), C_NULL, 0.0, 0.0, Int32(0), LIKE_NORMAL, sigma, LAYOUT_MU_ONLY,
+function DenseLinearModel(J::Matrix{Float64}, data::Vector{Float64}; sigma::Union{Real,Vector{Float64}}=0.5,
+                          ctx::B200Context=b200_context())
+    # a vector `sigma` (one noise level per datum) is folded into the operand load of the J'FJ tensor-core GEMM
+    sv = sigma isa Vector ? sigma : Float64[]
+    desc = ModelDesc(MODEL_DENSE_LINEAR, Int32(0), (0, 0, 0), C_NULL, 0.0, 0.0, Int32(0), LIKE_NORMAL,
+                     sigma isa Vector ? sigma[1] : Float64(sigma), LAYOUT_MU_ONLY,
                      pointer(data), length(data), Int32(0), C_NULL, C_NULL, Int32(0), C_NULL, 0.0, pointer(J),
-                     size(J, 1), size(J, 2))
-    DenseLinearModel(_create(ctx, desc, J, data))
+                     size(J, 1), size(J, 2), isempty(sv) ? C_NULL : pointer(sv), _NOHYPER...)
+    DenseLinearModel(_create(ctx, desc, J, data, sv))
+end
+
+"""
+    HyperFieldModel(kdist, scale, data_idxs, grain, binsize, data; a0, a1, l0, l1)
+
+The tutorial's model (docs/src/advanced_tutorial_lit.jl:194-307): `θ = [p₁, p₂, ξ]`, `sqrt_kernel` amplitude
+`a0·exp(a1·p₁)·√(2π·cl)·exp(-π²k²cl²)` with `cl = l0·exp(l1·p₂)`, `gp_sample`, `exp` link, `agg_lambdas` over
+`grain` fine pixels per data bin, Poisson counts.  `data_idxs` are `_DATA_IDXS` (1-based, regular).
+"""
+struct HyperFieldModel <: B200Model
+    handle::ModelHandle
+end
+
+function HyperFieldModel(kdist::Vector{Float64}, scale::Real, data_idxs::AbstractVector{<:Integer}, grain::Integer,
+                         binsize::Real, data::AbstractVector{<:Real}; a0::Real, a1::Real, l0::Real, l1::Real,
+                         ctx::B200Context=b200_context())
+    d = Float64.(data)
+    all(diff(data_idxs) .== grain) || error("HyperFieldModel: data bins must be regular (start + grain * b)")
+    N = length(kdist)
+    desc = ModelDesc(MODEL_FIELD_HYPER, Int32(1), (Int64(N), 0, 0), C_NULL, Float64(scale), 0.0, LINK_EXP, LIKE_POISSON, 1.0,
+                     LAYOUT_MU_ONLY, pointer(d), length(d), Int32(0), C_NULL, C_NULL, Int32(0), C_NULL, 0.0, C_NULL, 0, 0,
+                     C_NULL, pointer(kdist), (Float64(a0), Float64(a1), Float64(l0), Float64(l1)),
+                     Int64(first(data_idxs) - 1), Int32(grain), Float64(binsize))
+    HyperFieldModel(_create(ctx, desc, kdist, d))
 end
 
 (m::B200Model)(ξ) = error("declarative B200 models are evaluated on the device; there is no CPU fallback")

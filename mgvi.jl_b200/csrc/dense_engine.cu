@@ -21,7 +21,8 @@ namespace mgvi {
 
 static const int kNb = 64;     // Cholesky / triangular-solve block size
 
-SIMT_GLOBAL2(256, 1) k_dmma_gemm(SIMT_KARGS(GemmParams)) { SIMT_SMEM_DECL gemm_body(P, simt_smem); }
+template <bool KW>
+SIMT_GLOBAL2(256, 1) k_dmma_gemm(SIMT_KARGS(GemmParams)) { SIMT_SMEM_DECL gemm_body<KW>(P, simt_smem); }
 
 struct TriParams {
     double* A; long long ld;      // matrix holding the nb x nb diagonal block at (j0, j0)
@@ -177,7 +178,8 @@ struct DenseChol {
         g.kweight = kweight;
         g.ntm = (Mr + kGemmBM - 1) / kGemmBM; g.ntn = (Nc + kGemmBN - 1) / kGemmBN;
         ctx->prof_pre(3000 + (upper_only ? 1 : 0));
-        rt_launch(k_dmma_gemm, (long long)g.ntm * g.ntn, 256, sizeof(double) * 2 * kGemmBM * kGemmLd, ctx->stream, g);
+        if (kweight) rt_launch(k_dmma_gemm<true>, (long long)g.ntm * g.ntn, 256, sizeof(double) * 2 * kGemmBM * kGemmLd, ctx->stream, g);
+        else rt_launch(k_dmma_gemm<false>, (long long)g.ntm * g.ntn, 256, sizeof(double) * 2 * kGemmBM * kGemmLd, ctx->stream, g);
         ctx->prof_post();
         ctx->launches++;
     }

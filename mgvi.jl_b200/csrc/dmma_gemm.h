@@ -51,6 +51,7 @@ SIMT_DEVICE void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
 // Global -> registers for one 128 x 16 operand slab.  `kcontig`: the K index is the contiguous one.
 // Each thread fetches 8 doubles: kcontig: (row = t/8 + 32 r, k = 2 (t%8) + {0,1}), r = 0..3
 //                                 else   : (row = 2 (t%64) + {0,1}, k = t/64 + 4 r),   r = 0..3
+template <bool KW>
 SIMT_DEVICE void gemm_fetch(double (&reg)[8], const double* __restrict__ X, long long s_row, long long s_k, int row0,
                             int k0, int nrow, int nk, bool kcontig, const double* __restrict__ kweight = nullptr) {
     const int t = SIMT_TID;
@@ -63,7 +64,7 @@ SIMT_DEVICE void gemm_fetch(double (&reg)[8], const double* __restrict__ X, long
             else { row = 2 * (t & 63) + e; k = (t >> 6) + 4 * r; }
             const bool ok = (row0 + row < nrow) && (k0 + k < nk);
             double xv = ok ? X[(long long)(row0 + row) * s_row + (long long)(k0 + k) * s_k] : 0.0;
-            if (kweight && ok) xv *= SIMT_LDG(kweight + k0 + k);
+            if (KW) { if (ok) xv *= SIMT_LDG(kweight + k0 + k); }
             reg[2 * r + e] = xv;
         }
     }
@@ -83,6 +84,7 @@ SIMT_DEVICE void gemm_stash(const double (&reg)[8], double* sm, bool kcontig) {
     }
 }
 
+template <bool KW>
 SIMT_DEVICE void gemm_body(const GemmParams& P, unsigned char* smem) {
     double* As = reinterpret_cast<double*>(smem);
     double* Bs = As + kGemmBM * kGemmLd;
@@ -100,15 +102,15 @@ SIMT_DEVICE void gemm_body(const GemmParams& P, unsigned char* smem) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
     double ra[8], rb[8];
-    gemm_fetch(ra, P.A, P.a_row, P.a_k, row0, 0, P.M, P.K, a_kc, P.kweight);
-    gemm_fetch(rb, P.B, P.b_col, P.b_k, col0, 0, P.N, P.K, b_kc);
+    gemm_fetch<KW>(ra, P.A, P.a_row, P.a_k, row0, 0, P.M, P.K, a_kc, P.kweight);
+    gemm_fetch<false>(rb, P.B, P.b_col, P.b_k, col0, 0, P.N, P.K, b_kc);
     for (int k0 = 0; k0 < P.K; k0 += kGemmBK) {
         gemm_stash(ra, As, a_kc);
         gemm_stash(rb, Bs, b_kc);
         SIMT_SYNC();
         if (k0 + kGemmBK < P.K) {
-            gemm_fetch(ra, P.A, P.a_row, P.a_k, row0, k0 + kGemmBK, P.M, P.K, a_kc, P.kweight);
-            gemm_fetch(rb, P.B, P.b_col, P.b_k, col0, k0 + kGemmBK, P.N, P.K, b_kc);
+            gemm_fetch<KW>(ra, P.A, P.a_row, P.a_k, row0, k0 + kGemmBK, P.M, P.K, a_kc, P.kweight);
+            gemm_fetch<false>(rb, P.B, P.b_col, P.b_k, col0, k0 + kGemmBK, P.N, P.K, b_kc);
         }
 #pragma unroll
         for (int kk = 0; kk < kGemmBK; kk += 4) {

@@ -225,4 +225,199 @@ SIMT_DEVICE void dht_combine_read(double2 (&v)[8], const LineView& lv, int lt, i
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Paired arrangement for lengths n = 4 * 8^s (log2 n = 2 mod 3: the 2048- and 256-point axes of the
+// benchmark shapes).  A thread's 8 registers hold
+//     slot t     : element jA + t * n/4,   jA = lt
+//     slot 4 + t : element jB + t * n/4,   jB = n/4 - lt   (thread 0: jB = n/8)          t = 0..3
+// so that an element k and its Hartley partner n - k sit in the SAME thread (slot t <-> slot 7 - t;
+// thread 0: slot t <-> slot (4 - t) & 3 and slot 4 + t <-> slot 7 - t).  The combine
+//     H(a)[k] + i H(b)[k] = 1/2 [ (1+i) Z[k] + (1-i) Z[n-k] ]
+// is linear, so it can be applied to the OUTPUT of a transform (Z = FFT(a + i b)) or -- because
+// Z[n-k] = FFT(index-reversed input)[k] -- to its INPUT (y[j] = 1/2[(1+i) z[j] + (1-i) z[n-j]], FFT(y) is
+// the Hartley pair directly).  With the radix-4 stage of the Stockham factorisation placed LAST
+// (8 . 8 . 8 . 4: its two butterflies jA, jB produce exactly the paired slots) or FIRST (4 . 8 . 8 . 8: its
+// two butterflies consume exactly the paired slots) the combine needs NO shared-memory exchange:
+//     fft_line_post : standard arrangement in  -> paired arrangement out   (then dht_combine_paired)
+//     fft_line_pre  : (dht_combine_paired, then) paired arrangement in -> standard arrangement out
+// each with three exchanges instead of the four (three stages + partner read) of fft_line_forward +
+// dht_combine_read: 25 % less shared-memory traffic on kernels that are bound by the L1 data pipe.
+// ------------------------------------------------------------------------------------------
+template <int LG>
+SIMT_DEVICE int paired_jB(int lt) { return lt ? ((1 << (LG - 2)) - lt) : (1 << (LG - 3)); }
+
+// v <- 2 * combine(v) in registers (output side: Hartley pair from Z; input side: y from z)
+SIMT_DEVICE void dht_combine_paired(double2 (&v)[8], int lt) {
+    double2 o[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const double2 pa = lt ? v[7 - t] : v[(4 - t) & 3];
+        const double2 pb = lt ? v[3 - t] : v[7 - t];
+        const double2 za = v[t], zb = v[4 + t];
+        o[t] = make_double2(za.x - za.y + pa.x + pa.y, za.x + za.y + pa.y - pa.x);
+        o[4 + t] = make_double2(zb.x - zb.y + pb.x + pb.y, zb.x + zb.y + pb.y - pb.x);
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = o[m];
+}
+
+// radix-8 input twiddles W^(j t), t = 1..7, from the table entry w1 = W^j (W^2j, W^4j by squaring)
+SIMT_DEVICE void r8_twiddle(double2 (&v)[8], double2 w1) {
+    const double2 w2 = cmul(w1, w1);
+    v[1] = cmul(v[1], w1);
+    v[2] = cmul(v[2], w2);
+    double2 w3 = cmul(w1, w2);
+    v[3] = cmul(v[3], w3);
+    const double2 w4 = cmul(w2, w2);
+    v[4] = cmul(v[4], w4);
+    w3 = cmul(w3, w4);                // W^7
+    v[7] = cmul(v[7], w3);
+    w3 = cmul(w1, w4);                // W^5
+    v[5] = cmul(v[5], w3);
+    w3 = cmul(w2, w4);                // W^6
+    v[6] = cmul(v[6], w3);
+}
+
+// exchange-specific chunk swizzles (tools/bank_conflicts_paired.py): 0 = the usual one, 1 = bits 4..5 folded
+// into bits 1..2 (first exchange of fft_line_post with side-by-side lines), 2 = none
+template <int SW>
+SIMT_DEVICE int xswz(int c, int lgL) {
+    return SW == 2 ? c : (SW == 1 ? (c ^ ((c >> 3) & 6)) : swz(c, lgL));
+}
+
+// Standard arrangement in (v[m] = x[lt + m n/8]), paired arrangement out (slot t = Z[jA + t n/4],
+// slot 4 + t = Z[jB + t n/4]).  twp: per radix-8 stage with Ns = 8, 64, ... one run of Ns entries W^j
+// (W = exp(-2 pi i / (8 Ns))), then n/4 entries exp(-2 pi i j / n) for the final radix-4 stage.
+// Every thread of the block must call (uniform barriers).  Leaves no pending shared-memory reads.
+template <int LG>
+SIMT_DEVICE void fft_line_post(double2 (&v)[8], const LineView& lv, int lt, const double2* __restrict__ twp) {
+    static_assert(LG % 3 == 2 && LG >= 8, "paired transforms: n = 4 * 8^s, n >= 256");
+    constexpr int n8 = 1 << (LG - 3), n4 = 1 << (LG - 2);
+    const int lgL = lv.lgL;
+    const int rd_step = n8 << lgL;
+    const int std0 = ((lt << lgL) | lv.l);
+#pragma unroll
+    for (int lgNs = 0; lgNs + 2 < LG; lgNs += 3) {
+        const bool first = (lgNs == 0), last = (lgNs + 5 >= LG);
+        const int jlo = lt & ((1 << lgNs) - 1);
+        if (lgNs > 0) r8_twiddle(v, SIMT_LDG(twp + (((1 << lgNs) - 8) / 7) + jlo));
+        dft8(v);
+        const int base = ((lt >> lgNs) << (lgNs + 3)) | jlo;
+        const int cb = (base << lgL) | lv.l;
+        const int sh = lgNs + lgL;
+        if (last) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) lv.sm[cb + (t << sh)] = v[t];
+        } else if (first) {
+            if (lgL == 0) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) lv.sm[xswz<0>(cb + (t << sh), lgL)] = v[t];
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) lv.sm[xswz<1>(cb + (t << sh), lgL)] = v[t];
+            }
+        } else {
+            // middle exchanges: t << sh is a multiple of 64 chunks here (sh >= 3 + lgL ... checked below)
+            if (sh >= 6) {
+                const int w0 = xswz<0>(cb, lgL);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) lv.sm[w0 + (t << sh)] = v[t];
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) lv.sm[xswz<0>(cb + (t << sh), lgL)] = v[t];
+            }
+        }
+        SIMT_SYNC();
+        if (!last) {
+            // linear read-back in the standard arrangement (rd_step is a multiple of 64 chunks for n >= 512 or
+            // side-by-side lines; otherwise the swizzle is evaluated per element)
+            if ((rd_step & 63) == 0) {
+                const int r0 = (first && lgL != 0) ? xswz<1>(std0, lgL) : xswz<0>(std0, lgL);
+#pragma unroll
+                for (int m = 0; m < 8; ++m) v[m] = lv.sm[r0 + m * rd_step];
+            } else {
+#pragma unroll
+                for (int m = 0; m < 8; ++m)
+                    v[m] = lv.sm[(first && lgL != 0) ? xswz<1>(std0 + m * rd_step, lgL) : xswz<0>(std0 + m * rd_step, lgL)];
+            }
+            SIMT_SYNC();
+        }
+    }
+    // paired read for the final radix-4 stage (plain positions: descending runs straddle 8-chunk blocks)
+    const int jB = paired_jB<LG>(lt);
+    const int a0 = (lt << lgL) | lv.l, b0 = (jB << lgL) | lv.l;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        v[t] = lv.sm[a0 + ((t * n4) << lgL)];
+        v[4 + t] = lv.sm[b0 + ((t * n4) << lgL)];
+    }
+    SIMT_SYNC();
+    const double2* twf = twp + (n4 - 8) / 7;
+    {
+        const double2 w1 = SIMT_LDG(twf + lt);
+        const double2 w2 = cmul(w1, w1);
+        v[1] = cmul(v[1], w1);
+        v[2] = cmul(v[2], w2);
+        v[3] = cmul(v[3], cmul(w1, w2));
+        dft4(v[0], v[1], v[2], v[3]);
+    }
+    {
+        const double2 w1 = SIMT_LDG(twf + jB);
+        const double2 w2 = cmul(w1, w1);
+        v[5] = cmul(v[5], w1);
+        v[6] = cmul(v[6], w2);
+        v[7] = cmul(v[7], cmul(w1, w2));
+        dft4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+// Paired arrangement in (slot t = y[jA + t n/4], slot 4 + t = y[jB + t n/4]), standard arrangement out
+// (v[m] = Z[lt + m n/8], registers only: nothing is left in shared memory).  tw: the per-stage table of
+// fft_line_forward (stages Ns = 4, 32, ..., n/8).
+template <int LG>
+SIMT_DEVICE void fft_line_pre(double2 (&v)[8], const LineView& lv, int lt, const double2* __restrict__ tw) {
+    static_assert(LG % 3 == 2 && LG >= 8, "paired transforms: n = 4 * 8^s, n >= 256");
+    constexpr int n8 = 1 << (LG - 3);
+    const int lgL = lv.lgL;
+    const int rd_step = n8 << lgL;
+    const bool rd_fast = (rd_step & 63) == 0;
+    const int rd0 = lv.idx(lt);
+    const int jB = paired_jB<LG>(lt);
+    // leading radix-4 stage (Ns = 1): butterflies jA = lt and jB
+    dft4(v[0], v[1], v[2], v[3]);
+    dft4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        lv.at((lt << 2) + t) = v[t];
+        lv.at((jB << 2) + t) = v[4 + t];
+    }
+    SIMT_SYNC();
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = lv.sm[rd_fast ? rd0 + m * rd_step : lv.idx(lt + m * n8)];
+    SIMT_SYNC();
+#pragma unroll
+    for (int lgNs = 2; lgNs < LG; lgNs += 3) {
+        const int jlo = lt & ((1 << lgNs) - 1);
+        r8_twiddle(v, SIMT_LDG(tw + 3 * (((1 << lgNs) - 4) / 7) + jlo));
+        dft8(v);
+        if (lgNs + 3 < LG) {
+            const int base = ((lt >> lgNs) << (lgNs + 3)) | jlo;
+            const int cb = (base << lgL) | lv.l;
+            const int sh = lgNs + lgL;
+            if (sh >= 6) {
+                const int w0 = swz(cb, lgL);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) lv.sm[w0 + (t << sh)] = v[t];
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) lv.sm[swz(cb + (t << sh), lgL)] = v[t];
+            }
+            SIMT_SYNC();
+#pragma unroll
+            for (int m = 0; m < 8; ++m) v[m] = lv.sm[rd_fast ? rd0 + m * rd_step : lv.idx(lt + m * n8)];
+            SIMT_SYNC();
+        }
+    }
+}
+
 }  // namespace mgvi

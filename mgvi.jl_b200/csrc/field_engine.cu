@@ -48,6 +48,7 @@ struct FieldEngine : Engine {
     int prefetch_waves = 0;     // software L2 prefetch distance in resident-block waves (0 = off: measured slower at C3, profiles/README.md)
     bool use_hot = true;        // compile-time-shape kernels for the benchmark sizes
     int prefetch_epi = 0;       // L1 hints for post-transform operands (MGVIB200_PREFETCH_EPI)
+    bool use_paired = true;     // paired-arrangement transforms in the hot kernels (MGVIB200_PF=0: classic scheme)
     int stage_vin = 0;          // TMA bulk staging of the '+ v' rows in the hot last pass (needs -DMGVI_STAGE_VIN; MGVIB200_STAGE_VIN=1)
 
     DevBuf A, data, w, q, wbar, center, w_tiled, ws_tile;
@@ -56,7 +57,7 @@ struct FieldEngine : Engine {
     int w_tiled_lg_wt = 0;
     int row_threads = 256;      // target block size of the row (contiguous) passes (MGVIB200_ROW_THREADS)
     int tiled_mode = -1;        // tile-major scratch for 2-D narrow column tiles: -1 auto, 0 off, 1 force (MGVIB200_TILED)
-    std::map<long long, DevBuf> tw, cas;
+    std::map<long long, DevBuf> tw, twp, cas;     // twp: tables of the paired transforms (n = 4 * 8^s)
     ReduceWs rws;
     CgWs cgws, ncgws;
     DevBuf ws_r, ws_p, ws_t;          // sampler CG vectors [nvec][N]
@@ -96,6 +97,7 @@ struct FieldEngine : Engine {
                          &n_p, &n_t, &tmpA, &tmpB, &rws.partials, &rws.counters, &rws.red};
         for (auto* b : all) b->release();
         for (auto& kv : tw) kv.second.release();
+        for (auto& kv : twp) kv.second.release();
         for (auto& kv : cas) kv.second.release();
         DevBuf* cg[] = {&cgws.gamma, &cgws.alpha, &cgws.beta, &cgws.eps, &cgws.rnorm, &cgws.pAp, &cgws.iters,
                         &cgws.active, &cgws.n_active, &ncgws.gamma, &ncgws.alpha, &ncgws.beta, &ncgws.eps,
@@ -142,6 +144,7 @@ struct FieldEngine : Engine {
         if (const char* e = getenv("MGVIB200_STAGE_VIN")) stage_vin = atoi(e);
         if (const char* e = getenv("MGVIB200_TILED")) tiled_mode = atoi(e);
         if (const char* e = getenv("MGVIB200_GRAPH")) graphs_on = atoi(e) != 0;
+        if (const char* e = getenv("MGVIB200_PF")) use_paired = atoi(e) != 0;
         if (const char* e = getenv("MGVIB200_ROW_THREADS")) row_threads = std::max(32, atoi(e));
         if (getenv("MGVIB200_FORCE_GENERIC") && atoi(getenv("MGVIB200_FORCE_GENERIC"))) big = false;
         if (!fast)
@@ -190,6 +193,24 @@ struct FieldEngine : Engine {
                 tw[n].ensure(sizeof(double) * t.size());
                 rt_h2d(tw[n].p, t.data(), sizeof(double) * t.size(), ctx->stream);
                 rt_sync(ctx->stream);
+                if (lead == 2 && lg >= 8) {
+                    // paired transforms (fft_core.h: fft_line_post): radix-8 stages Ns = 8, 64, ... (one run W^j each),
+                    // then the final radix-4 stage: exp(-2 pi i j / n), j < n/4
+                    std::vector<double> u;
+                    const long double tp = 2.0L * 3.14159265358979323846264338327950288L;
+                    for (long long Ns = 8; 8 * Ns <= n / 4; Ns *= 8)
+                        for (long long j = 0; j < Ns; ++j) {
+                            const long double a = tp * (long double)j / (long double)(8 * Ns);
+                            u.push_back((double)cosl(a)); u.push_back((double)(-sinl(a)));
+                        }
+                    for (long long j = 0; j < n / 4; ++j) {
+                        const long double a = tp * (long double)j / (long double)n;
+                        u.push_back((double)cosl(a)); u.push_back((double)(-sinl(a)));
+                    }
+                    twp[n].ensure(sizeof(double) * u.size());
+                    rt_h2d(twp[n].p, u.data(), sizeof(double) * u.size(), ctx->stream);
+                    rt_sync(ctx->stream);
+                }
             } else {
                 if (cas.count(n)) continue;
                 std::vector<double> t((size_t)n * n);
@@ -267,7 +288,7 @@ struct FieldEngine : Engine {
         B.f = P;
         const size_t smem = kSmemHeader + (size_t)G * ((size_t)16 << (lgL + lg_len));
         ctx->prof_pre(5000 + KIND * 100 + PRO * 10 + EPI);
-        rt_launch(k_big1d<KIND, PRO, EPI>, grid, (int)(G * upt), smem, ctx->stream, B);
+        rt_launch_pdl(k_big1d<KIND, PRO, EPI>, grid, (int)(G * upt), smem, ctx->stream, B);
         ctx->prof_post();
         ctx->launches++;
     }
@@ -330,14 +351,24 @@ struct FieldEngine : Engine {
     template <int GEO, int PRO, int EPI, bool DBL>
     void launch_lg(const FieldPassParams& P, const PassGeo& g, long long grid) {
         if (g.threads <= 256)
-            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 256, 2, 0, -1, true>, grid, g.threads, g.smem, ctx->stream, P);
+            rt_launch_pdl(k_field_pass<GEO, PRO, EPI, DBL, 256, 2, 0, -1, true>, grid, g.threads, g.smem, ctx->stream, P);
         else if (g.threads <= 512)
-            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 512, 1, 0, -1, true>, grid, g.threads, g.smem, ctx->stream, P);
+            rt_launch_pdl(k_field_pass<GEO, PRO, EPI, DBL, 512, 1, 0, -1, true>, grid, g.threads, g.smem, ctx->stream, P);
         else
-            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 1024, 1, 0, -1, true>, grid, g.threads, g.smem, ctx->stream, P);
+            rt_launch_pdl(k_field_pass<GEO, PRO, EPI, DBL, 1024, 1, 0, -1, true>, grid, g.threads, g.smem, ctx->stream, P);
     }
 
     // compile-time-shape build; the block size follows from (LG, LGL): 2^(LG - 3 + LGL) threads per unit
+    template <int GEO, int PRO, int EPI, bool DBL, int LG, int LGL, int PF>
+    void launch_hot_pf(const FieldPassParams& P, const PassGeo& g, long long grid) {
+        if (g.threads <= 256)
+            rt_launch_pdl(k_field_pass<GEO, PRO, EPI, DBL, 256, MGVI_MINB, LG, LGL, false, PF>, grid, g.threads, g.smem, ctx->stream, P);
+        else if (g.threads <= 512)
+            rt_launch_pdl(k_field_pass<GEO, PRO, EPI, DBL, 512, 2, LG, LGL, false, PF>, grid, g.threads, g.smem, ctx->stream, P);
+        else
+            rt_launch_pdl(k_field_pass<GEO, PRO, EPI, DBL, 1024, 1, LG, LGL, false, PF>, grid, g.threads, g.smem, ctx->stream, P);
+    }
+
     template <int GEO, int PRO, int EPI, bool DBL, int LG, int LGL>
     void launch_hot(const FieldPassParams& P0, const PassGeo& g0, long long grid) {
         FieldPassParams P = P0;
@@ -349,14 +380,20 @@ struct FieldEngine : Engine {
             g.smem = (size_t)field_pass_smem_bytes_staged(g.n, g.L, g.G);
         }
 #endif
-        constexpr int upt = (LG > 0) ? (1 << (LG - 3 + LGL)) : 256;
-        (void)upt;
-        if (g.threads <= 256)
-            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 256, MGVI_MINB, LG, LGL, false>, grid, g.threads, g.smem, ctx->stream, P);
-        else if (g.threads <= 512)
-            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 512, 2, LG, LGL, false>, grid, g.threads, g.smem, ctx->stream, P);
-        else
-            rt_launch(k_field_pass<GEO, PRO, EPI, DBL, 1024, 1, LG, LGL, false>, grid, g.threads, g.smem, ctx->stream, P);
+        // transform scheme of this kernel (field_pass.h): the paired schemes drop one shared-memory exchange per
+        // transform; first pass of a CG iteration = 1, last pass = 2, fused axis-0 pass = 3
+        constexpr int PF = (LG % 3 != 2 || LG < 8) ? 0
+                           : (GEO == GEO_CONTIG && PRO == PRO_CG && EPI == EPI_STORE) ? 1
+                           : (GEO == GEO_CONTIG && PRO == PRO_LOAD && EPI == EPI_METRIC) ? 2
+                           : (GEO == GEO_STRIDED && DBL) ? 3 : 0;
+        if constexpr (PF != 0) {
+            if (use_paired && !P.stage_vin) {
+                P.tw2 = twp.at(g.n).as<double2>();
+                launch_hot_pf<GEO, PRO, EPI, DBL, LG, LGL, PF>(P, g, grid);
+                return;
+            }
+        }
+        launch_hot_pf<GEO, PRO, EPI, DBL, LG, LGL, 0>(P, g, grid);
     }
 
     template <int GEO, int PRO, int EPI, bool DBL>

@@ -49,6 +49,7 @@ struct FieldPassParams {
     long long N, inner, units_per_vec, ntb;
     int nvec, nsgrp, nloop;
     const double2* tw;
+    const double2* tw2;                       // paired transforms (fft_core.h: fft_line_post), lengths 4 * 8^s
     // ---- operands -------------------------------------------------------------------------
     const double* in;  long long in_ld;
     double* out;       long long out_ld;
@@ -230,9 +231,12 @@ SIMT_DEVICE void epi_pair(const FieldPassParams& P, int sa, int sb, long long pa
 // pipeline (and re-reads beta for every element); here every batch issues all its loads first,
 // through __restrict__ pointers, then computes, then stores.
 // ------------------------------------------------------------------------------------------
+// Slot 4 h + j of a thread's 8 elements sits at offset off + h * d1 + j * stepj: the standard arrangement
+// (k = lt + m n/8) is d1 = 4 step, stepj = step; the paired arrangement (fft_core.h) is d1 = (jB - jA) * kstride,
+// stepj = 2 step.
 template <bool ADJ>
 SIMT_DEVICE void pro_cg_block(double2 (&v)[8], double* __restrict__ p, const double* __restrict__ r,
-                              const double* __restrict__ A, unsigned off_a, unsigned off_b, unsigned step,
+                              const double* __restrict__ A, unsigned off_a, unsigned off_b, int d1, unsigned stepj,
                               long long vec_off, double beta, bool first_iter) {
     // p = r + beta p (skipped on the first iteration, where p = r already) ; v = A . p
 #pragma unroll
@@ -240,7 +244,7 @@ SIMT_DEVICE void pro_cg_block(double2 (&v)[8], double* __restrict__ p, const dou
         double2 pp[4], rr[4], aa[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const unsigned oa = off_a + (4 * h + j) * step, ob = off_b + (4 * h + j) * step;
+            const unsigned oa = off_a + h * d1 + j * stepj, ob = off_b + h * d1 + j * stepj;
             pp[j] = ld_pair(p, vec_off + oa, vec_off + ob, true, true, ADJ);
             aa[j] = ldg_pair(A, oa, ob, true, true, ADJ);
             if (!first_iter) rr[j] = ld_pair(r, vec_off + oa, vec_off + ob, true, true, ADJ);
@@ -248,7 +252,7 @@ SIMT_DEVICE void pro_cg_block(double2 (&v)[8], double* __restrict__ p, const dou
         if (!first_iter) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const unsigned oa = off_a + (4 * h + j) * step, ob = off_b + (4 * h + j) * step;
+                const unsigned oa = off_a + h * d1 + j * stepj, ob = off_b + h * d1 + j * stepj;
                 pp[j] = make_double2(rr[j].x + beta * pp[j].x, rr[j].y + beta * pp[j].y);
                 st_pair(p, vec_off + oa, vec_off + ob, true, true, ADJ, pp[j]);
             }
@@ -287,7 +291,7 @@ SIMT_DEVICE void epi_metric_block_staged(const double2 (&v)[8], double* __restri
 
 template <bool ADJ>
 SIMT_DEVICE void epi_metric_block(const double2 (&v)[8], double* __restrict__ out, const double* __restrict__ vin,
-                                  const double* __restrict__ A, unsigned off_a, unsigned off_b, unsigned step,
+                                  const double* __restrict__ A, unsigned off_a, unsigned off_b, int d1, unsigned stepj,
                                   long long out_off, long long vin_off, double scale, double& acc) {
     // out = vin + scale * A . val ; acc += vin . out
 #pragma unroll
@@ -295,13 +299,13 @@ SIMT_DEVICE void epi_metric_block(const double2 (&v)[8], double* __restrict__ ou
         double2 vi[4], aa[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const unsigned oa = off_a + (4 * h + j) * step, ob = off_b + (4 * h + j) * step;
+            const unsigned oa = off_a + h * d1 + j * stepj, ob = off_b + h * d1 + j * stepj;
             vi[j] = ld_pair(vin, vin_off + oa, vin_off + ob, true, true, ADJ);
             aa[j] = ld_pair(A, oa, ob, true, true, ADJ);       // plain load: must not be hoisted above the transform
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const unsigned oa = off_a + (4 * h + j) * step, ob = off_b + (4 * h + j) * step;
+            const unsigned oa = off_a + h * d1 + j * stepj, ob = off_b + h * d1 + j * stepj;
             const double2 val = v[4 * h + j];
             const double2 o = make_double2(vi[j].x + scale * (aa[j].x * val.x), vi[j].y + scale * (aa[j].y * val.y));
             st_pair(out, out_off + oa, out_off + ob, true, true, ADJ, o);
@@ -436,7 +440,12 @@ SIMT_HD long long field_pass_smem_bytes_staged(int n, int L, int G) {
 // LG > 0 / LGL >= 0 fix log2(n) / log2(L) at compile time; LOOP = false drops the loop over vectors
 // (nloop == 1): with everything known the shared-memory swizzle offsets fold into immediates and
 // nothing loop-invariant is left for the compiler to hoist and spill.
-template <int GEO, int PRO, int EPI, bool DOUBLE, int LG, int LGL, bool LOOP>
+// PF selects the transform scheme (fft_core.h): 0 = fft_line_forward + partner read; the paired schemes
+// (hot kernels of the 2048- / 256-point axes only) drop one shared-memory exchange per transform:
+//   1 = operands loaded in the paired arrangement, combine on the INPUT, standard arrangement out (first pass)
+//   2 = standard arrangement in, combine on the OUTPUT in registers, epilogue in the paired arrangement (last pass)
+//   3 = DOUBLE: scheme 2, mid weight in the paired arrangement, scheme 1 (fused axis-0 pass)
+template <int GEO, int PRO, int EPI, bool DOUBLE, int LG, int LGL, bool LOOP, int PF = 0>
 SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_raw) {
     const int log2n = LG ? LG : P.log2n, lgL = (LGL >= 0) ? LGL : P.lgL;
     const int n8 = 1 << (log2n - 3);
@@ -496,8 +505,9 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
     }
 
     double acc_a = 0.0, acc_b = 0.0;
-    // element offsets of my 8 elements: off_a + m * step (and off_b + m * step)
-    unsigned off_a = 0, off_b = 0, step = (unsigned)n8;
+    // element offsets of my 8 elements: off_a + m * step (and off_b + m * step); kstr = offset of one step
+    // along the transform axis (step = n/8 * kstr)
+    unsigned off_a = 0, off_b = 0, step = (unsigned)n8, kstr = 1;
     bool unit_ok = true;
     if (!pairvec) {
         const long long u = bt * P.G + g;
@@ -511,16 +521,21 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
             // so the 2L-real row segments of this pass are back to back instead of one per 128-byte line
             off_a = (unsigned)((u << (lgL + 1 + log2n)) + ((long long)lt << (lgL + 1)) + 2 * l);
             off_b = off_a + 1;
+            kstr = 1u << (lgL + 1);
             step = (unsigned)(n8 << (lgL + 1));
         } else {
             const long long o = u >> P.lg_tpo, cb = u & ((1LL << P.lg_tpo) - 1);
             off_a = (unsigned)(((o << log2n) + lt) * P.inner + (cb << (lgL + 1)) + 2 * l);
             off_b = off_a + 1;
+            kstr = (unsigned)P.inner;
             step = (unsigned)(n8 * P.inner);
         }
     } else {
         off_a = off_b = (unsigned)lt;
     }
+    // paired arrangement (PF != 0): slot 4 h + j at off + h * pd1 + j * 2 step
+    int pd1 = 0;
+    if (PF != 0) pd1 = (paired_jB<(LG > 0 ? LG : 8)>(lt) - lt) * (int)kstr;
     // row passes next to a tile-major column pass: the scratch operand (the output of the first
     // pass, the input of the last) is addressed tile-major -- element (row r, column k) lives at
     // (k / wt) * wt * rows + r * wt + k % wt; rows 2u and 2u+1 of a unit are wt reals apart
@@ -558,8 +573,12 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
                              : make_double2(0.0, 0.0);
         } else if (valid) {
             if (PRO == PRO_CG) {
-                pro_cg_block<GEO == GEO_STRIDED>(v, P.p, P.r, P.A, off_a, off_b, step, (long long)sa * P.N,
-                                                 P.first_iter ? 0.0 : P.cg.beta[sa], P.first_iter != 0);
+                if (PF == 1)
+                    pro_cg_block<GEO == GEO_STRIDED>(v, P.p, P.r, P.A, off_a, off_b, pd1, 2 * step, (long long)sa * P.N,
+                                                     P.first_iter ? 0.0 : P.cg.beta[sa], P.first_iter != 0);
+                else
+                    pro_cg_block<GEO == GEO_STRIDED>(v, P.p, P.r, P.A, off_a, off_b, 4 * (int)step, step, (long long)sa * P.N,
+                                                     P.first_iter ? 0.0 : P.cg.beta[sa], P.first_iter != 0);
             } else if (PRO == PRO_LOAD && GEO == GEO_CONTIG && P.t_lg_wt && n8 >= 32) {
                 // tile-major scratch, row pass: a unit's two rows sit wt reals apart, so lane pairs
                 // fetch 16 bytes of ONE row each (even lane: row a, columns k, k+1; odd lane: row b,
@@ -622,8 +641,16 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
             }
         }
         if (it > 0) SIMT_SYNC();   // previous iteration's combine reads vs this iteration's writes
-        fft_line_forward<LG>(v, lv, lt, log2n, P.tw);
-        dht_combine_read<LG>(v, lv, lt, log2n);
+        if (PF == 1) {
+            dht_combine_paired(v, lt);                     // combine on the input (zeros stay zeros)
+            fft_line_pre<(LG > 0 ? LG : 8)>(v, lv, lt, P.tw);
+        } else if (PF == 2 || PF == 3) {
+            fft_line_post<(LG > 0 ? LG : 8)>(v, lv, lt, P.tw2);
+            dht_combine_paired(v, lt);
+        } else {
+            fft_line_forward<LG>(v, lv, lt, log2n, P.tw);
+            dht_combine_read<LG>(v, lv, lt, log2n);
+        }
         SIMT_OPAQUE_U32(off_a); SIMT_OPAQUE_U32(off_b); SIMT_OPAQUE_U32(step);
         if (DOUBLE) {
             if (valid) {
@@ -636,17 +663,27 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
                         // plain (coherent) loads on purpose: read-only-path loads may be hoisted above the
                         // barriers to the top of the kernel, which keeps 32 registers live through the
                         // whole first transform and spills
-                        wv[j] = pairvec ? ld_pair(P.w, off_a + m * step, off_b + m * step, va, vb, false)
-                                        : ld_pair(P.w, off_a + m * step, off_b + m * step, true, true, adj);
+                        if (PF == 3) {
+                            const unsigned o = off_a + h * pd1 + j * 2 * step;
+                            wv[j] = ld_pair(P.w, o, o + 1, true, true, adj);
+                        } else {
+                            wv[j] = pairvec ? ld_pair(P.w, off_a + m * step, off_b + m * step, va, vb, false)
+                                            : ld_pair(P.w, off_a + m * step, off_b + m * step, true, true, adj);
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         v[4 * h + j] = make_double2(v[4 * h + j].x * wv[j].x, v[4 * h + j].y * wv[j].y);
                 }
             }
-            SIMT_SYNC();
-            fft_line_forward<LG>(v, lv, lt, log2n, P.tw);
-            dht_combine_read<LG>(v, lv, lt, log2n);
+            if (PF == 3) {
+                dht_combine_paired(v, lt);
+                fft_line_pre<(LG > 0 ? LG : 8)>(v, lv, lt, P.tw);
+            } else {
+                SIMT_SYNC();
+                fft_line_forward<LG>(v, lv, lt, log2n, P.tw);
+                dht_combine_read<LG>(v, lv, lt, log2n);
+            }
             SIMT_OPAQUE_U32(off_a); SIMT_OPAQUE_U32(off_b); SIMT_OPAQUE_U32(step);
         }
         if (valid) {
@@ -659,8 +696,12 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
                 epi_metric_block_staged(v, P.out, stg, P.A, off_a, off_b, step, (long long)sa * P.out_ld, lt, 1 << log2n,
                                         P.scale, acc_a);
             } else if (EPI == EPI_METRIC) {
-                epi_metric_block<GEO == GEO_STRIDED>(v, P.out, P.vin, P.A, off_a, off_b, step, (long long)sa * P.out_ld,
-                                                     (long long)sa * P.vin_ld, P.scale, acc_a);
+                if (PF == 2)
+                    epi_metric_block<GEO == GEO_STRIDED>(v, P.out, P.vin, P.A, off_a, off_b, pd1, 2 * step, (long long)sa * P.out_ld,
+                                                         (long long)sa * P.vin_ld, P.scale, acc_a);
+                else
+                    epi_metric_block<GEO == GEO_STRIDED>(v, P.out, P.vin, P.A, off_a, off_b, 4 * (int)step, step, (long long)sa * P.out_ld,
+                                                         (long long)sa * P.vin_ld, P.scale, acc_a);
             } else if (EPI == EPI_STORE && GEO == GEO_CONTIG && P.t_lg_wt && n8 >= 32) {
                 // tile-major scratch, row pass: the mirror image of the paired load above
                 const int q = lt & 1;

@@ -24,15 +24,17 @@ namespace mgvi {
 // MAXT = 256: up to 256 threads, MINB resident blocks per SM wanted; MAXT = 1024: wide tiles.
 // LG > 0 / LGL >= 0: log2 of the transform length / of the tile width fixed at compile time (hot
 // sizes), LOOP = false: one vector per block; LG = 0, LGL = -1, LOOP = true: everything at run time.
-template <int GEO, int PRO, int EPI, bool DOUBLE, int MAXT, int MINB, int LG, int LGL, bool LOOP>
+template <int GEO, int PRO, int EPI, bool DOUBLE, int MAXT, int MINB, int LG, int LGL, bool LOOP, int PF = 0>
 SIMT_GLOBAL2(MAXT, MINB) k_field_pass(SIMT_KARGS(FieldPassParams)) {
     SIMT_SMEM_DECL
-    field_pass_body<GEO, PRO, EPI, DOUBLE, LG, LGL, LOOP>(P, simt_smem);
+    SIMT_PDL_ENTRY();
+    field_pass_body<GEO, PRO, EPI, DOUBLE, LG, LGL, LOOP, PF>(P, simt_smem);
 }
 
 template <int KIND, int PRO, int EPI>
 SIMT_GLOBAL2(1024, 1) k_big1d(SIMT_KARGS(BigParams)) {
     SIMT_SMEM_DECL
+    SIMT_PDL_ENTRY();
     big1d_body<KIND, PRO, EPI>(P, simt_smem);
 }
 

@@ -78,6 +78,30 @@ inline void rt_launch(K kernel, long long grid, int block, size_t smem, rt_strea
     RT_CUDA(cudaGetLastError());
 }
 
+// Programmatic dependent launch (MGVIB200_PDL=1): the kernel may be scheduled while its predecessor in the
+// stream drains; it must execute SIMT_PDL_ENTRY() (griddepcontrol.wait) before touching global memory.  Only
+// kernels whose entry point does that are launched through here.
+inline bool rt_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("MGVIB200_PDL"); on = (e && atoi(e)) ? 1 : 0; }
+    return on == 1;
+}
+template <typename K, typename P>
+inline void rt_launch_pdl(K kernel, long long grid, int block, size_t smem, rt_stream s, const P& params) {
+    if (!rt_pdl_enabled()) { rt_launch(kernel, grid, block, smem, s, params); return; }
+    if (grid <= 0) return;
+    if (grid > 2147483647LL) throw RtError{"grid too large", 1};
+    if (smem > 48 * 1024) rt_ensure_smem_attr((const void*)kernel, smem);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    RT_CUDA(cudaLaunchKernelEx(&cfg, kernel, params));
+}
+
 // CUDA graphs: a fixed launch sequence (several lock-step CG iterations -- every per-iteration scalar
 // lives in device memory, so the kernel parameters do not change) captured once and replayed
 typedef cudaGraphExec_t rt_graph;
@@ -158,6 +182,12 @@ inline void rt_graph_launch(rt_graph, rt_stream) {}
 inline void rt_graph_destroy(rt_graph) {}
 inline void rt_event_sync(rt_event) {}
 
+template <typename K, typename P>
+inline void rt_launch(K kernel, long long grid, int block, size_t smem, rt_stream, const P& params);
+template <typename K, typename P>
+inline void rt_launch_pdl(K kernel, long long grid, int block, size_t smem, rt_stream s, const P& params) {
+    rt_launch(kernel, grid, block, smem, s, params);
+}
 template <typename K, typename P>
 inline void rt_launch(K kernel, long long grid, int block, size_t smem, rt_stream, const P& params) {
     if (grid <= 0) return;

@@ -52,6 +52,13 @@
 // addresses of a later phase at the top of the kernel
 #define SIMT_OPAQUE_U32(x) asm volatile("" : "+r"(x))
 #define SIMT_RSQRT(x) rsqrt(x)
+// programmatic dependent launch: let the successor be scheduled now, then wait until the predecessor grid has
+// completed and its writes are visible (a no-op when the kernel was not launched as a dependent)
+#define SIMT_PDL_ENTRY()                                                   \
+    do {                                                                   \
+        asm volatile("griddepcontrol.launch_dependents;");                 \
+        asm volatile("griddepcontrol.wait;" ::: "memory");                 \
+    } while (0)
 #define SIMT_KERNEL(name, params_t, body_call)                                   \
     __global__ void name(const params_t P) {                                     \
         extern __shared__ __align__(16) unsigned char simt_smem[];               \
@@ -81,6 +88,7 @@
 #define SIMT_PREFETCH_L1(ptr) ((void)0)
 #define SIMT_OPAQUE_U32(x) ((void)0)
 #define SIMT_RSQRT(x) (1.0 / sqrt(x))
+#define SIMT_PDL_ENTRY() ((void)0)
 #define SIMT_MBAR_INIT(mbar, count) ((void)0)
 #define SIMT_BULK_G2S(dst, src, bytes, mbar) memcpy((dst), (src), (bytes))
 #define SIMT_MBAR_WAIT(mbar, parity) ((void)0)

@@ -7,6 +7,7 @@ namespace mgvi {
 
 SIMT_GLOBAL(256) k_vec(SIMT_KARGS(VecParams)) {
     SIMT_SMEM_DECL
+    SIMT_PDL_ENTRY();
     vec_body(P, simt_smem);
 }
 
@@ -35,7 +36,7 @@ void vec_launch(mgvib200_ctx* ctx, ReduceWs& ws, VecParams P) {
         if (!P.red_out) P.red_out = ws.red.as<double>();
     }
     ctx->prof_pre(1000 + P.op);
-    rt_launch(k_vec, grid, kVecThreads, 512, ctx->stream, P);
+    rt_launch_pdl(k_vec, grid, kVecThreads, 512, ctx->stream, P);
     ctx->prof_post();
     ctx->launches++;
 }

@@ -134,13 +134,18 @@ def _step_errors(got, rec, om, R, check_wbar, k):
 
 
 class _Reassociated:
-    """The oracle model with J v and J' l evaluated through the materialised Jacobian in a permuted row order:
-    the same reference formula v + J'(F . (J v)) summed in a different (equally valid) order.  A backward-
-    stable matvec is reproducible to eps ||M|| ||u||, which for an ill-scaled metric (polynomial fit: entries
-    1e6 ... 1e10 next to the unit prior) is far more than what a one-ulp change of the INPUTS produces."""
+    """The oracle model with the metric product evaluated the way ANOTHER valid implementation of the same
+    reference formula v + J'(F . (J v)) would round it: J v and J' l through the materialised Jacobian in a
+    permuted row order, and every lambda-space component carrying the rounding of a length-n_lambda reduction
+    done in a different order (relative sqrt(n_lambda) eps, random sign) -- the device reduces over the data
+    points block-wise where NumPy sums pairwise.  A backward-stable product is only reproducible to
+    ~ sqrt(N) eps ||M|| ||u||, which for an ill-scaled metric (polynomial fit: eigenvalues 8 ... 4e7, measured
+    normwise difference device vs oracle 3.6e-15) is far more than a one-ulp change of the INPUTS produces:
+    the 5th update of a 5 x 5 CG then moves by O(1) (measured: both sides' 5th iterates are 5 % / 35 % off the
+    exact solve while iterates 1-4 agree to 1e-17 ... 8e-10)."""
 
     def __init__(self, om, seed):
-        self._om, self._seed = om, seed
+        self._om, self._seed, self._calls = om, seed, 0
 
     def __getattr__(self, name):
         return getattr(self._om, name)
@@ -151,8 +156,14 @@ class _Reassociated:
         perm = np.random.default_rng(self._seed).permutation(J.shape[0])
         inv = np.argsort(perm)
         Jp = np.ascontiguousarray(J[perm])
-        return O.mgvi_oracle.Linearization(lin.n_theta, lin.n_lambda, lin.fisher, lambda v: (Jp @ v)[inv], lambda l: Jp.T @ l[perm],
-                               lin.dense)
+        amp = np.sqrt(J.shape[0]) * np.finfo(float).eps
+
+        def jvp(v):
+            self._calls += 1
+            noise = np.random.default_rng((self._seed, self._calls)).standard_normal(J.shape[0])
+            return (Jp @ v)[inv] * (1.0 + amp * noise)
+
+        return O.mgvi_oracle.Linearization(lin.n_theta, lin.n_lambda, lin.fisher, jvp, lambda l: Jp.T @ l[perm], lin.dense)
 
 
 def _oracle_step_sensitivity(om, R, rec, opts, nseeds=None):

@@ -127,3 +127,30 @@ def test_julia_shim_matches_the_header():
         assert name in proto, "shim calls undeclared symbol %s" % name
         ntypes = _top_level_count(_balanced(jl, m.end() - 1))
         assert ntypes == proto[name], (name, ntypes, proto[name])
+
+
+def test_model_descriptor_layouts_agree():
+    """The model descriptor is declared three times (C header, ctypes mirror, Julia shim): same fields, same
+    order -- a field appended in one place only would shift every later member."""
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    py = [f[0] for f in pkg.capi.ModelDesc._fields_]
+    hdr = open(os.path.join(ROOT, "include", "mgvi_b200.h")).read()
+    body = hdr[hdr.index("typedef struct {\n    int32_t kind;"):hdr.index("} mgvib200_model_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    c = []
+    for stmt in body.split(";"):
+        stmt = stmt.strip()
+        if not stmt or stmt.startswith("typedef"):
+            stmt = stmt.replace("typedef struct {", "").strip()
+            if not stmt:
+                continue
+        decls = stmt.split(",")
+        c.append(re.search(r"([a-z_A-Z0-9]+)(?:\[\d+\])?\s*$", decls[0].strip()).group(1))
+        c += [re.search(r"([a-z_A-Z0-9]+)(?:\[\d+\])?\s*$", d.strip()).group(1) for d in decls[1:]]
+    assert c == py, (c, py)
+    jl = open(os.path.join(ROOT, "julia", "MGVIB200.jl")).read()
+    jb = jl[jl.index("struct ModelDesc\n"):]
+    jb = jb[:jb.index("\nend")]
+    j = [m.group(1) for m in re.finditer(r"^\s+([a-z_A-Z0-9]+)::", jb, flags=re.M)]
+    assert j == py, (j, py)

@@ -396,7 +396,19 @@ def test_coal_mining_tutorial_run(pkg, gpu_ctx):
         assert rtol_R < 1e-2, (it, sens)
         # teacher-forced: the device's step from the oracle's centre
         res, cn = pkg.mgvi_step(m, cfg["data"], n, c_or, conf, gpu_ctx, draws=(Z1, Z2))
-        assert res.info["linsolver_output"]["iters"].tolist() == ref["sampler_iters"].tolist(), it
+        it_dev, it_ref = res.info["linsolver_output"]["iters"], ref["sampler_iters"]
+        if it_dev.tolist() != it_ref.tolist():
+            # ||r|| sits on the atol = 1e-2 threshold within the amplified rounding (and is not monotone in CG): a
+            # sample may stop a few iterations apart (seen: 12 vs 10 at a measured oracle reproducibility of 7e-5).
+            # Compare against the oracle stopped at the DEVICE's counts -- same algorithm, same draws.
+            assert np.abs(it_dev - it_ref).max() <= 3 and sens > 1e-12, (it, it_dev, it_ref, sens)
+            Rr = ref["residuals"].copy()
+            for i in np.nonzero(it_dev != it_ref)[0]:
+                Ri, iti, _ = O.sample_residuals_cg(om, c_or, Z1[:, [i]], Z2[:, [i]], atol=0.0, rtol=0.0, itmax=int(it_dev[i]))
+                assert int(iti[0]) == int(it_dev[i])
+                Rr[:, i] = Ri[:, 0]
+            xo, fo, tro = O.newtoncg_optimize(om, Rr, c_or, O.NewtonCGOpts(**ncg_kw))
+            ref = dict(samples=O.build_samples(Rr, xo), mnlp=fo, center=xo, residuals=Rr, sampler_iters=it_dev, trace=tro)
         step_cfg = dict(cfg, center=c_or)
         assert_step_parity(pkg, m, om, step_cfg, res, cn, ref, label="coal mining it %d" % it, opts_kw=ncg_kw,
                            residual_tol=rtol_R)

@@ -31,9 +31,14 @@ def main():
     syn = pkg.synthetic
     ok = True
     # 1-D fields pair two residuals per complex transform: an even number per rank (16 / 8 ranks)
-    for dims, like, n in [((256, 256), syn.LIKE_NORMAL, 8), ((4096,), syn.LIKE_POISSON, 16), ((32, 32, 32), syn.LIKE_POISSON, 8),
-                          ((65536,), syn.LIKE_POISSON, 16)]:
-        cfg = syn.field_config(dims, like, n, field_std=0.5)
+    counts = np.load(os.path.join(ROOT, "tests", "golden", "coal_mining_counts.npz"))["counts"]
+    cases = [syn.field_config(dims, like, n, field_std=0.5)
+             for dims, like, n in [((256, 256), syn.LIKE_NORMAL, 8), ((4096,), syn.LIKE_POISSON, 16),
+                                   ((32, 32, 32), syn.LIKE_POISSON, 8), ((65536,), syn.LIKE_POISSON, 16)]]
+    # the tutorial's hyperparameter field: per-sample metrics, canonical sum of n_theta-vectors across ranks
+    cases.append(syn.hyper_field_config(counts, 8, start_scale=0.3))
+    for cfg in cases:
+        dims, n = cfg.get("dims", ("hyper", cfg["n_theta"])), cfg["n_residuals"]
         ctx = pkg.MGVIContext(device=local)
         box = [ctx.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
