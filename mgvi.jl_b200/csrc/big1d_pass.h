@@ -45,9 +45,12 @@ SIMT_DEVICE long long big_logical(const BigParams& B, long long pix) {
     return r + (c << B.lg_n1);
 }
 
+// `vbid` >= 0: the block index to act as (persistent kernel: a resident block walks over the block indices of
+// a phase); -1: the hardware block index.
 template <int KIND, int PRO, int EPI>
-SIMT_DEVICE void big1d_body(const BigParams& B, unsigned char* smem_raw) {
+SIMT_DEVICE void big1d_body(const BigParams& B, unsigned char* smem_raw, long long vbid = -1) {
     const FieldPassParams& P = B.f;
+    const long long BID = vbid >= 0 ? vbid : SIMT_BID;
     const int lg_len = (KIND == BIG_A || KIND == BIG_AP) ? B.lg_n1 : B.lg_n2;     // transform length of this kernel
     const int n8 = 1 << (lg_len - 3);
     const int lgL = B.lgL;
@@ -67,8 +70,8 @@ SIMT_DEVICE void big1d_body(const BigParams& B, unsigned char* smem_raw) {
 
     // block -> (unit block, pair group); units of a block share the pair
     const long long ubl = (B.units_per_pair + B.G - 1) / B.G;
-    const long long bt = SIMT_BID % ubl;
-    const long long pgrp = SIMT_BID / ubl;
+    const long long bt = BID % ubl;
+    const long long pgrp = BID / ubl;
     const long long u = bt * B.G + g;
     const bool unit_ok = u < B.units_per_pair;
 
@@ -79,9 +82,20 @@ SIMT_DEVICE void big1d_body(const BigParams& B, unsigned char* smem_raw) {
     if (KIND == BIG_A) {
         col = (u << lgL) + l; base = col; stride = n2;
     } else if (KIND == BIG_AP) {
-        // column pair (u, n2 - u); unit 0 holds the two self-mirrored columns 0 and n2/2
-        if (u == 0) { col = l ? (n2 >> 1) : 0; self_pair = true; }
-        else col = l ? (n2 - u) : u;
+        if (lgL == 1) {
+            // column pair (u, n2 - u); unit 0 holds the two self-mirrored columns 0 and n2/2
+            if (u == 0) { col = l ? (n2 >> 1) : 0; self_pair = true; }
+            else col = l ? (n2 - u) : u;
+        } else {
+            // H = 2^(lgL-1) neighbouring columns u H .. u H + H-1 (lines 0..H-1) and their mirrors (lines H..2H-1,
+            // line H + i <-> column n2 - (u H + i)): whole 32-byte sectors per row instead of one double per
+            // sector.  Column 0 mirrors onto itself; its mirror slot holds the other self-mirrored column n2/2.
+            const int H = 1 << (lgL - 1), i = l & (H - 1);
+            const long long cdir = u * H + i;
+            if (l < H) col = cdir;
+            else col = (cdir == 0) ? (n2 >> 1) : (n2 - cdir);
+            self_pair = (cdir == 0);
+        }
         base = col; stride = n2;
     } else {
         if (u == 0) { row = l ? (n1 >> 1) : 0; self_pair = true; }
@@ -102,6 +116,36 @@ SIMT_DEVICE void big1d_body(const BigParams& B, unsigned char* smem_raw) {
         double2* cs = B.cs + pair * n;
         double2 v[8];
         // ---------------- load ----------------
+        if (KIND == BIG_A && PRO == PRO_CG && valid) {
+            // CG iteration: p = r + beta p, v = A . p -- all loads of the thread's 8 elements first, then the
+            // stores (the per-element form alternates loads with stores to arrays that may alias and pays one
+            // memory round trip per element)
+            double* __restrict__ pA = P.p + (long long)sa * P.N;
+            double* __restrict__ pB = P.p + (long long)sb * P.N;
+            const double* __restrict__ rA = P.r + (long long)sa * P.N;
+            const double* __restrict__ rB = P.r + (long long)sb * P.N;
+            double2 pp[8], rr[8];
+            double aa[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const long long pix = base + (long long)(lt + m * n8) * stride;
+                pp[m] = make_double2(va ? pA[pix] : 0.0, vb ? pB[pix] : 0.0);
+                aa[m] = SIMT_LDG(P.A + pix);
+                if (!P.first_iter) rr[m] = make_double2(va ? rA[pix] : 0.0, vb ? rB[pix] : 0.0);
+            }
+            if (!P.first_iter) {
+                const double ba = va ? P.cg.beta[sa] : 0.0, bb = vb ? P.cg.beta[sb] : 0.0;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const long long pix = base + (long long)(lt + m * n8) * stride;
+                    pp[m] = make_double2(rr[m].x + ba * pp[m].x, rr[m].y + bb * pp[m].y);
+                    if (va) pA[pix] = pp[m].x;
+                    if (vb) pB[pix] = pp[m].y;
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < 8; ++m) v[m] = make_double2(aa[m] * pp[m].x, aa[m] * pp[m].y);
+        } else
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             const long long pix = base + (long long)(lt + m * n8) * stride;
@@ -143,7 +187,7 @@ SIMT_DEVICE void big1d_body(const BigParams& B, unsigned char* smem_raw) {
         // ---------------- Hartley combine with the mirrored line ----------------
         {
             LineView pv = lv;
-            pv.l = self_pair ? l : (l ^ 1);
+            pv.l = self_pair ? l : ((KIND == BIG_AP) ? (l ^ (1 << (lgL - 1))) : (l ^ 1));
             const long long len = 1LL << lg_len;
             // partner position along the line: the line with index 0 (row 0 / column 0) mirrors onto itself
             // with (len - k) mod len; every other line mirrors with len - 1 - k
@@ -174,7 +218,28 @@ SIMT_DEVICE void big1d_body(const BigParams& B, unsigned char* smem_raw) {
             continue;
         }
         // ---------------- epilogue (BIG_B_END in permuted data space, BIG_AP in natural order) ----------------
-        if (valid) {
+        if (valid && EPI == EPI_METRIC) {
+            // out = vin + scale * A . val ; acc += vin . out -- loads first, then stores (see the CG prologue above)
+            const double* __restrict__ iA = P.vin + (long long)sa * P.vin_ld;
+            const double* __restrict__ iB = P.vin + (long long)sb * P.vin_ld;
+            double* __restrict__ oA = P.out + (long long)sa * P.out_ld;
+            double* __restrict__ oB = P.out + (long long)sb * P.out_ld;
+            double2 vi[8];
+            double aa[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const long long pix = base + (long long)(lt + m * n8) * stride;
+                vi[m] = make_double2(va ? iA[pix] : 0.0, vb ? iB[pix] : 0.0);
+                aa[m] = SIMT_LDG(P.A + pix);
+            }
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const long long pix = base + (long long)(lt + m * n8) * stride;
+                const double2 o = make_double2(vi[m].x + P.scale * (aa[m] * v[m].x), vi[m].y + P.scale * (aa[m] * v[m].y));
+                if (va) { oA[pix] = o.x; acc_a += vi[m].x * o.x; }
+                if (vb) { oB[pix] = o.y; acc_b += vi[m].y * o.y; }
+            }
+        } else if (valid) {
 #pragma unroll
             for (int m = 0; m < 8; ++m) {
                 const long long pix = base + (long long)(lt + m * n8) * stride;
@@ -188,7 +253,7 @@ SIMT_DEVICE void big1d_body(const BigParams& B, unsigned char* smem_raw) {
     if (P.fin == FIN_NONE) return;
     if (P.fin == FIN_TOTAL) {
         const double tot = seg_reduce(acc_a + acc_b, SIMT_NTID, red);
-        block_publish_and_finalize(P.fin, P.cg, P.red_out, P.partials, P.counters, 0, SIMT_BID, SIMT_NBID, tot, red,
+        block_publish_and_finalize(P.fin, P.cg, P.red_out, P.partials, P.counters, 0, BID, SIMT_NBID, tot, red,
                                    flag);
     } else {
         // per-vector reductions (CG dots): blocks of one pair group publish two partials each

@@ -179,6 +179,9 @@ void vec_cg_init(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, const dou
                  double* r, double* p, long long N, int nvec);
 void vec_cg_update(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* x, double* r, const double* p,
                    const double* Ap, long long N, int nvec);
+// the same update as kernel parameters + block count, for kernels that run it as one of their phases
+VecParams vec_cg_update_params(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* x, double* r,
+                               const double* p, const double* Ap, long long N, int nvec, long long* grid);
 
 }  // namespace mgvi
 

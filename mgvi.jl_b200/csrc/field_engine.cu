@@ -85,6 +85,13 @@ struct FieldEngine : Engine {
     CgGraphKey cg_graph_key{};
     int64_t cg_graph_launches = 0;
     bool graphs_on = true;          // MGVIB200_GRAPH=0 launches every kernel from the host
+    int big_ap_lgL = 3;             // MGVIB200_BIG_AP_LGL: log2(lines per unit) of the column kernel A' (1 = one column pair)
+    // MGVIB200_PERSIST=1: one persistent cooperative kernel per solve for L2-resident long 1-D fields.  Measured on
+    // B200 (profiles/README.md, round 2): C2 0.0599 ms per iteration against 0.0491 ms for the CUDA-graph replay of the
+    // stand-alone kernels -- the four phases inlined into one kernel spill ~700 bytes at 128 registers while each
+    // stand-alone kernel fits, which costs more than the three kernel boundaries it saves.  Off by default.
+    bool persist_on = false;
+    DevBuf pbar, pparams;           // grid barrier counter and parameter block of the persistent kernel
     CgScalars ncg_sc;
     bool ncg_first = true;
     int h_ncg[2] = {0, 0};
@@ -94,7 +101,7 @@ struct FieldEngine : Engine {
         dense_chol_destroy(chol);
         Mdense.release(); eye.release();
         DevBuf* all[] = {&A, &data, &w, &q, &wbar, &center, &w_tiled, &ws_tile, &ws_r, &ws_p, &ws_t, &pt_t, &gather, &sc_gather, &kl_red, &qsum, &n_x, &n_r,
-                         &n_p, &n_t, &tmpA, &tmpB, &rws.partials, &rws.counters, &rws.red};
+                         &n_p, &n_t, &tmpA, &tmpB, &pbar, &pparams, &cs, &tlo, &thi, &data_perm, &rws.partials, &rws.counters, &rws.red};
         for (auto* b : all) b->release();
         for (auto& kv : tw) kv.second.release();
         for (auto& kv : twp) kv.second.release();
@@ -145,6 +152,8 @@ struct FieldEngine : Engine {
         if (const char* e = getenv("MGVIB200_TILED")) tiled_mode = atoi(e);
         if (const char* e = getenv("MGVIB200_GRAPH")) graphs_on = atoi(e) != 0;
         if (const char* e = getenv("MGVIB200_PF")) use_paired = atoi(e) != 0;
+        if (const char* e = getenv("MGVIB200_PERSIST")) persist_on = atoi(e) != 0;
+        if (const char* e = getenv("MGVIB200_BIG_AP_LGL")) big_ap_lgL = std::min(3, std::max(1, atoi(e)));
         if (const char* e = getenv("MGVIB200_ROW_THREADS")) row_threads = std::max(32, atoi(e));
         if (getenv("MGVIB200_FORCE_GENERIC") && atoi(getenv("MGVIB200_FORCE_GENERIC"))) big = false;
         if (!fast)
@@ -253,9 +262,13 @@ struct FieldEngine : Engine {
     // ------------------------------------------------------------------------------------------
     // long 1-D fields (big1d_pass.h)
     // ------------------------------------------------------------------------------------------
-    template <int KIND, int PRO, int EPI>
-    void launch_big(FieldPassParams P, int nvec) {
-        BigParams B;
+    struct BigLaunch { BigParams B; long long grid; int threads; size_t smem; };
+
+    // geometry and operands of one kernel of the four-step path (no launch)
+    template <int KIND>
+    BigLaunch prep_big(FieldPassParams P, int nvec) {
+        BigLaunch L;
+        BigParams& B = L.B;
         memset(&B, 0, sizeof B);
         const int npairs = (nvec + 1) / 2;
         cs.ensure(16 * (size_t)N * npairs);
@@ -264,13 +277,16 @@ struct FieldEngine : Engine {
         B.tw1 = tw.at(1LL << lg_n1).as<double2>(); B.tw2 = tw.at(1LL << lg_n2).as<double2>();
         B.tlo = tlo.as<double2>(); B.thi = thi.as<double2>();
         const int lg_len = (KIND == BIG_A || KIND == BIG_AP) ? lg_n1 : lg_n2;
-        int lgL = (KIND == BIG_A) ? 2 : 1;
-        while (lg_len - 3 + lgL > 10) --lgL;                                   // <= 1024 threads per unit
+        // lines side by side per unit: A: 4 neighbouring columns; A': 4 neighbouring columns + their 4 mirrors
+        // (big_ap_lgL, 1 = one column pair); B kernels: a row and its mirror
+        int lgL = (KIND == BIG_A) ? 2 : ((KIND == BIG_AP) ? big_ap_lgL : 1);
+        while (lgL > 1 && (lg_len - 3 + lgL > 10 || ((size_t)16 << (lgL + lg_len)) > 200 * 1024 ||
+                           (KIND == BIG_AP && (1LL << lg_n2) < (4LL << lgL)))) --lgL;   // <= 1024 threads per unit
         if (KIND != BIG_A && lg_len - 3 + lgL > 10) throw RtError{"1-D field too long for the four-step path", 3};
         B.lgL = lgL;
         const long long upt = 1LL << (lg_len - 3 + lgL);
         long long G = std::max<long long>(1, 256 / upt);
-        B.units_per_pair = (KIND == BIG_A) ? ((1LL << lg_n2) >> lgL) : ((KIND == BIG_AP) ? ((1LL << lg_n2) >> 1) : ((1LL << lg_n1) >> 1));
+        B.units_per_pair = (KIND == BIG_A) ? ((1LL << lg_n2) >> lgL) : ((KIND == BIG_AP) ? ((1LL << lg_n2) >> lgL) : ((1LL << lg_n1) >> 1));
         G = std::min(G, B.units_per_pair);
         G = std::max<long long>(G, (32 + upt - 1) / upt);
         B.G = (int)G;
@@ -278,17 +294,25 @@ struct FieldEngine : Engine {
         const int npgrp = npairs;
         B.nloop = 1;
         const long long ubl = (B.units_per_pair + G - 1) / G;
-        const long long grid = ubl * npgrp;
+        L.grid = ubl * npgrp;
         P.N = N; P.nvec = nvec;
         if (P.fin != FIN_NONE) {
-            const size_t np = (P.fin == FIN_TOTAL) ? (size_t)grid : (size_t)(nvec + 1) * (size_t)ubl;
+            const size_t np = (P.fin == FIN_TOTAL) ? (size_t)L.grid : (size_t)(nvec + 1) * (size_t)ubl;
             reduce_ws_ensure(rws, ctx, np, (size_t)nvec + 1);
             P.partials = rws.partials.as<double>(); P.counters = rws.counters.as<unsigned>();
         }
         B.f = P;
-        const size_t smem = kSmemHeader + (size_t)G * ((size_t)16 << (lgL + lg_len));
+        L.threads = (int)(G * upt);
+        L.smem = kSmemHeader + (size_t)G * ((size_t)16 << (lgL + lg_len));
+        return L;
+    }
+
+    template <int KIND, int PRO, int EPI>
+    void launch_big(FieldPassParams P, int nvec) {
+        const BigLaunch L = prep_big<KIND>(P, nvec);
         ctx->prof_pre(5000 + KIND * 100 + PRO * 10 + EPI);
-        rt_launch_pdl(k_big1d<KIND, PRO, EPI>, grid, (int)(G * upt), smem, ctx->stream, B);
+        if (L.threads <= 256) rt_launch_pdl(k_big1d<KIND, PRO, EPI, 256>, L.grid, L.threads, L.smem, ctx->stream, L.B);
+        else rt_launch_pdl(k_big1d<KIND, PRO, EPI, 1024>, L.grid, L.threads, L.smem, ctx->stream, L.B);
         ctx->prof_post();
         ctx->launches++;
     }
@@ -752,7 +776,8 @@ struct FieldEngine : Engine {
         if (h[0] > 0 && itmax > 0) {
             launch_iter(true);
             it = 1;
-            const bool use_graph = rt_has_graphs && graphs_on && !ctx->profile;
+            if (it < itmax && sample_cg_persistent(sc, R, nvec, itmax - 1)) it = itmax;
+            const bool use_graph = rt_has_graphs && graphs_on && !ctx->profile && it < itmax;
             if (use_graph) {
                 const CgGraphKey key{R, ws_r.p, ws_p.p, ws_t.p, ws_tile.p, w_tiled.p, nvec, o.abstol, o.reltol, itmax};
                 if (!cg_graph_valid || !(key == cg_graph_key)) {
@@ -772,7 +797,9 @@ struct FieldEngine : Engine {
                     cg_graph_valid = true;
                 }
             }
-            if (!use_graph) {
+            if (it >= itmax) {
+                // all remaining iterations ran inside the persistent kernel
+            } else if (!use_graph) {
                 // host-launched iterations (emulator build, per-kernel profiling, MGVIB200_GRAPH=0): poll after
                 // 1, 2, 4, 8, 8, ... iterations
                 int poll = 1;
@@ -816,6 +843,59 @@ struct FieldEngine : Engine {
             mx = std::max<long long>(mx, hi[i]);
         }
         ctx->lockstep_iters = mx;
+    }
+
+    // Long 1-D fields whose CG state stays in L2 (C2): every iteration after the first in ONE cooperative launch
+    // (kernels.h: k_big1d_cg_persist).  Returns false when the shape does not qualify; the caller then runs the
+    // graph / host-launched sequence.  Same kernels bodies, same launch geometry per phase, same results.
+    bool sample_cg_persistent(const CgScalars& sc, double* R, int nvec, long long max_iters) {
+#if defined(__CUDACC__) && !defined(MGVI_SIMT_EMU)
+        if (!big || !rt_has_coop || !persist_on || ctx->profile) return false;
+        if ((size_t)N * nvec * sizeof(double) > ((size_t)32 << 20)) return false;
+        BigCgParams Q;
+        memset(&Q, 0, sizeof Q);
+        size_t smem = 512;
+        bool ok = true;
+        for (int pass = 0; pass < 2; ++pass) {         // second pass: the reduction workspace no longer moves
+            FieldPassParams P = base_params();
+            P.r = ws_r.as<double>(); P.p = ws_p.as<double>();
+            P.vin = ws_p.as<double>(); P.vin_ld = N;
+            P.out = ws_t.as<double>(); P.out_ld = N;
+            P.w = w.as<double>();
+            P.first_iter = 0;
+            P.cg = sc;
+            P.mask_active = 1;
+            P.scale = c * c * pow(0.5, 2 * ndim);
+            FieldPassParams E = P;
+            E.fin = FIN_CG_PAP; E.red_out = nullptr;
+            P.fin = FIN_NONE;
+            const BigLaunch a = prep_big<BIG_A>(P, nvec), b = prep_big<BIG_B_MID>(P, nvec), ap = prep_big<BIG_AP>(E, nvec);
+            Q.a = a.B; Q.b = b.B; Q.ap = ap.B;
+            Q.grid_a = a.grid; Q.grid_b = b.grid; Q.grid_ap = ap.grid;
+            Q.u = vec_cg_update_params(ctx, rws, sc, R, ws_r.as<double>(), ws_p.as<double>(), ws_t.as<double>(), N, nvec, &Q.grid_u);
+            ok = (a.threads == 256 && b.threads == 256 && ap.threads == 256);
+            smem = std::max(std::max(a.smem, b.smem), std::max(ap.smem, (size_t)512));
+        }
+        if (!ok) return false;
+        const long long cap = rt_max_coresident(k_big1d_cg_persist<0>, 256, smem);
+        if (cap < ctx->sm_count) return false;
+        const long long want = std::max(std::max(Q.grid_a, Q.grid_b), std::max(Q.grid_ap, Q.grid_u));
+        const long long grid = std::min(want, cap);
+        pbar.ensure(64);
+        rt_memset(pbar.p, 0, 64, ctx->stream);
+        Q.bar = pbar.as<unsigned>();
+        Q.max_iters = max_iters;
+        pparams.ensure(sizeof Q);
+        rt_h2d(pparams.p, &Q, sizeof Q, ctx->stream);
+        rt_sync(ctx->stream);                 // Q is a stack object
+        const BigCgParams* Qd = pparams.as<BigCgParams>();
+        rt_launch_coop(k_big1d_cg_persist<0>, grid, 256, smem, ctx->stream, Qd);
+        ctx->launches++;
+        return true;
+#else
+        (void)sc; (void)R; (void)nvec; (void)max_iters;
+        return false;
+#endif
     }
 
     // MatrixInversion (src/residual_samplers.jl:95-123): the reference materialises M = J'FJ + I by n_theta

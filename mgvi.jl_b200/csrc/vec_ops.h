@@ -94,11 +94,13 @@ SIMT_DEVICE void vec_elem(const VecParams& P, int s, long long i, double alpha, 
 }
 
 // block -> (chunk, vector); a block covers `per_block` consecutive elements of one vector.
-SIMT_DEVICE void vec_body(const VecParams& P, unsigned char* smem_raw) {
+// `vbid` >= 0: the block index to act as (persistent kernels); -1: the hardware block index.
+SIMT_DEVICE void vec_body(const VecParams& P, unsigned char* smem_raw, long long vbid = -1) {
     double* red = reinterpret_cast<double*>(smem_raw);
     int* flag = reinterpret_cast<int*>(smem_raw + 256);
-    const int s = (int)(SIMT_BID % P.nvec);
-    const long long chunk = SIMT_BID / P.nvec;
+    const long long BID = vbid >= 0 ? vbid : SIMT_BID;
+    const int s = (int)(BID % P.nvec);
+    const long long chunk = BID / P.nvec;
     const bool cg_op = (P.op == VOP_CG_UPDATE || P.op == VOP_CG_PUPD || P.op == VOP_CG_PAP);
     if (cg_op && !P.cg.active[s]) return;
     const double alpha = (P.op == VOP_CG_UPDATE) ? P.cg.alpha[s] : 0.0;
@@ -114,14 +116,27 @@ SIMT_DEVICE void vec_body(const VecParams& P, unsigned char* smem_raw) {
         const double2* __restrict__ a2 = reinterpret_cast<const double2*>(P.Ap + base);
         double2* __restrict__ x2 = reinterpret_cast<double2*>(P.x + base);
         double2* __restrict__ r2 = reinterpret_cast<double2*>(P.r + base);
-        for (long long i = (lo >> 1) + SIMT_TID; i < (hi >> 1); i += SIMT_NTID) {
-            const double2 pv = p2[i], av = a2[i];
-            double2 xv = x2[i], rv = r2[i];
-            xv.x += alpha * pv.x; xv.y += alpha * pv.y;
-            rv.x -= alpha * av.x; rv.y -= alpha * av.y;
-            x2[i] = xv; r2[i] = rv;
-            acc += rv.x * rv.x;
-            acc += rv.y * rv.y;
+        // four independent 16-byte quadruples in flight per thread (the loop is a chain of memory round trips
+        // when the vectors are L2-resident); the order of the additions into acc is that of the plain loop
+        const long long i1 = hi >> 1, nt = SIMT_NTID;
+        for (long long i0 = (lo >> 1) + SIMT_TID; i0 < i1; i0 += 4 * nt) {
+            double2 pv[4], av[4], xv[4], rv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long i = i0 + u * nt;
+                if (i < i1) { pv[u] = p2[i]; av[u] = a2[i]; xv[u] = x2[i]; rv[u] = r2[i]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long i = i0 + u * nt;
+                if (i < i1) {
+                    xv[u].x += alpha * pv[u].x; xv[u].y += alpha * pv[u].y;
+                    rv[u].x -= alpha * av[u].x; rv[u].y -= alpha * av[u].y;
+                    x2[i] = xv[u]; r2[i] = rv[u];
+                    acc += rv[u].x * rv[u].x;
+                    acc += rv[u].y * rv[u].y;
+                }
+            }
         }
     } else {
         for (long long i = lo + SIMT_TID; i < hi; i += SIMT_NTID) vec_elem(P, s, i, alpha, acc);
@@ -129,7 +144,7 @@ SIMT_DEVICE void vec_body(const VecParams& P, unsigned char* smem_raw) {
     if (P.fin == FIN_NONE) return;
     const double tot = seg_reduce(acc, SIMT_NTID, red);
     if (P.fin == FIN_TOTAL)
-        block_publish_and_finalize(P.fin, P.cg, P.red_out, P.partials, P.counters, 0, SIMT_BID, SIMT_NBID, tot, red,
+        block_publish_and_finalize(P.fin, P.cg, P.red_out, P.partials, P.counters, 0, BID, SIMT_NBID, tot, red,
                                    flag);
     else
         block_publish_and_finalize(P.fin, P.cg, P.red_out, P.partials, P.counters, s, chunk, P.nchunk, tot, red,
