@@ -49,6 +49,7 @@ WORKLOADS = {
     "c2": ((65536,), "LIKE_POISSON", 16),
     "c5": ((256, 256, 256), "LIKE_POISSON", 64),
     "small": ((256, 256), "LIKE_NORMAL", 8),
+    "np2": ((1000, 1000), "LIKE_NORMAL", 8),      # axis lengths that are not a power of two (Bluestein passes)
 }
 
 

@@ -14,12 +14,19 @@ SIMT_GLOBAL(256) k_naive_axis(SIMT_KARGS(NaiveParams)) {
     naive_axis_body(P, simt_smem);
 }
 
+template <int MAXT>
+SIMT_GLOBAL2(MAXT, (MAXT <= 256 ? 2 : 1)) k_bluestein_axis(SIMT_KARGS(BlueParams)) {
+    SIMT_SMEM_DECL
+    bluestein_axis_body(P, simt_smem);
+}
+
 namespace {
 
 #ifndef MGVI_MINB
 #define MGVI_MINB 3      // resident 256-thread blocks per SM the pass kernels are compiled for
 #endif
 const int kNaiveMaxAxis = 4096;
+long long kBlueMinAxis = 32;           // (MGVIB200_BLUE_MIN overrides: measurements against the direct pass) generic path: axes longer than this take the O(m log m) Bluestein pass, shorter ones the direct O(n^2) one
 const long long kFastMaxAxis = 4096;
 const long long kDenseFieldMax = 8192;
 
@@ -58,6 +65,7 @@ struct FieldEngine : Engine {
     int row_threads = 256;      // target block size of the row (contiguous) passes (MGVIB200_ROW_THREADS)
     int tiled_mode = -1;        // tile-major scratch for 2-D narrow column tiles: -1 auto, 0 off, 1 force (MGVIB200_TILED)
     std::map<long long, DevBuf> tw, twp, cas;     // twp: tables of the paired transforms (n = 4 * 8^s)
+    std::map<long long, DevBuf> blue_chirp, blue_hf;   // any-length axes: Bluestein chirp and filter spectrum
     ReduceWs rws;
     CgWs cgws, ncgws;
     DevBuf ws_r, ws_p, ws_t;          // sampler CG vectors [nvec][N]
@@ -70,12 +78,16 @@ struct FieldEngine : Engine {
     DenseChol* chol = nullptr;
     // replayable chunk of the sampler's lock-step CG iterations (sample_cg)
     struct CgGraphKey {
-        const void *R, *r, *p, *t, *tile, *wt;
+        // every buffer a captured kernel may point into: the CG vectors, the pass scratch, the staging buffers of
+        // the generic and four-step paths and the reduction workspace (all of them can be re-allocated larger by a
+        // later call with more vectors, e.g. a KL evaluation over 2n points)
+        const void *R, *r, *p, *t, *tile, *wt, *ta, *tb, *cs, *part, *cnt;
         int nvec;
         double atol, rtol;
         long long itmax;
         bool operator==(const CgGraphKey& o) const {
-            return R == o.R && r == o.r && p == o.p && t == o.t && tile == o.tile && wt == o.wt && nvec == o.nvec &&
+            return R == o.R && r == o.r && p == o.p && t == o.t && tile == o.tile && wt == o.wt && ta == o.ta &&
+                   tb == o.tb && cs == o.cs && part == o.part && cnt == o.cnt && nvec == o.nvec &&
                    atol == o.atol && rtol == o.rtol && itmax == o.itmax;
         }
     };
@@ -85,6 +97,7 @@ struct FieldEngine : Engine {
     CgGraphKey cg_graph_key{};
     int64_t cg_graph_launches = 0;
     bool graphs_on = true;          // MGVIB200_GRAPH=0 launches every kernel from the host
+    int big_block_threads = 64;     // (measured at C2: 64 -> 0.0475 ms per iteration, 256 -> 0.0490) MGVIB200_BIG_THREADS: target block size of the four-step kernels (units per block = this / unit size)
     int big_ap_lgL = 3;             // MGVIB200_BIG_AP_LGL: log2(lines per unit) of the column kernel A' (1 = one column pair)
     // MGVIB200_PERSIST=1: one persistent cooperative kernel per solve for L2-resident long 1-D fields.  Measured on
     // B200 (profiles/README.md, round 2): C2 0.0599 ms per iteration against 0.0491 ms for the CUDA-graph replay of the
@@ -106,10 +119,100 @@ struct FieldEngine : Engine {
         for (auto& kv : tw) kv.second.release();
         for (auto& kv : twp) kv.second.release();
         for (auto& kv : cas) kv.second.release();
+        for (auto& kv : blue_chirp) kv.second.release();
+        for (auto& kv : blue_hf) kv.second.release();
         DevBuf* cg[] = {&cgws.gamma, &cgws.alpha, &cgws.beta, &cgws.eps, &cgws.rnorm, &cgws.pAp, &cgws.iters,
                         &cgws.active, &cgws.n_active, &ncgws.gamma, &ncgws.alpha, &ncgws.beta, &ncgws.eps,
                         &ncgws.rnorm, &ncgws.pAp, &ncgws.iters, &ncgws.active, &ncgws.n_active};
         for (auto* b : cg) b->release();
+    }
+
+    // per-stage twiddle runs of the power-of-two FFT core (fft_core.h) for length n, built once per length
+    void build_fft_tables(long long n) {
+        if (tw.count(n)) return;
+        // for each radix-8 stage with Ns > 1: W^j, W^2j, W^4j, j < Ns
+        std::vector<double> t;
+        const int lg = ilog2(n), lead = lg % 3;
+        for (int lgNs = lead; lgNs < lg; lgNs += 3) {
+            if (lgNs == 0) continue;
+            const long long Ns = 1LL << lgNs;
+            for (int e = 1; e <= 4; e *= 2)
+                for (long long j = 0; j < Ns; ++j) {
+                    long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)(e * j) /
+                                    (long double)(8 * Ns);
+                    t.push_back((double)cosl(a));
+                    t.push_back((double)(-sinl(a)));
+                }
+        }
+        if (t.empty()) { t.push_back(1.0); t.push_back(0.0); }
+        tw[n].ensure(sizeof(double) * t.size());
+        rt_h2d(tw[n].p, t.data(), sizeof(double) * t.size(), ctx->stream);
+        rt_sync(ctx->stream);
+        if (lead == 2 && lg >= 8) {
+            // paired transforms (fft_core.h: fft_line_post): radix-8 stages Ns = 8, 64, ... (one run W^j each),
+            // then the final radix-4 stage: exp(-2 pi i j / n), j < n/4
+            std::vector<double> u;
+            const long double tp = 2.0L * 3.14159265358979323846264338327950288L;
+            for (long long Ns = 8; 8 * Ns <= n / 4; Ns *= 8)
+                for (long long j = 0; j < Ns; ++j) {
+                    const long double a = tp * (long double)j / (long double)(8 * Ns);
+                    u.push_back((double)cosl(a)); u.push_back((double)(-sinl(a)));
+                }
+            for (long long j = 0; j < n / 4; ++j) {
+                const long double a = tp * (long double)j / (long double)n;
+                u.push_back((double)cosl(a)); u.push_back((double)(-sinl(a)));
+            }
+            twp[n].ensure(sizeof(double) * u.size());
+            rt_h2d(twp[n].p, u.data(), sizeof(double) * u.size(), ctx->stream);
+            rt_sync(ctx->stream);
+        }
+    }
+
+    // Bluestein tables for an axis of any length n (field_pass.h: bluestein_axis_body): the chirp c_j =
+    // exp(-i pi j^2 / n) and the length-m FFT of the wrapped conjugate chirp, scaled by 1/m, in long double
+    static int blue_lg_m(long long n) { int lg = 8; while ((1LL << lg) < 2 * n - 1) ++lg; return lg; }
+    void build_bluestein_tables(long long n) {
+        if (blue_chirp.count(n)) return;
+        const int lg_m = blue_lg_m(n);
+        const long long m = 1LL << lg_m;
+        build_fft_tables(m);
+        const long double pi = 3.14159265358979323846264338327950288L;
+        std::vector<long double> cr(n), ci(n);
+        for (long long j = 0; j < n; ++j) {
+            const long double a = pi * (long double)((j * j) % (2 * n)) / (long double)n;     // j^2 mod 2n keeps the argument small
+            cr[j] = cosl(a); ci[j] = -sinl(a);
+        }
+        std::vector<long double> hr(m, 0.0L), hi(m, 0.0L);
+        for (long long j = 0; j < n; ++j) {
+            hr[j] = cr[j]; hi[j] = -ci[j];
+            if (j) { hr[m - j] = cr[j]; hi[m - j] = -ci[j]; }
+        }
+        // iterative radix-2 FFT in long double (host, once per length)
+        for (long long i = 1, j = 0; i < m; ++i) {
+            long long bit = m >> 1;
+            for (; j & bit; bit >>= 1) j ^= bit;
+            j ^= bit;
+            if (i < j) { std::swap(hr[i], hr[j]); std::swap(hi[i], hi[j]); }
+        }
+        for (long long len = 2; len <= m; len <<= 1) {
+            for (long long k = 0; k < len / 2; ++k) {
+                const long double a = -2.0L * pi * (long double)k / (long double)len;
+                const long double wr = cosl(a), wi = sinl(a);
+                for (long long i = k; i < m; i += len) {
+                    const long long j2 = i + len / 2;
+                    const long double xr = hr[j2] * wr - hi[j2] * wi, xi = hr[j2] * wi + hi[j2] * wr;
+                    hr[j2] = hr[i] - xr; hi[j2] = hi[i] - xi;
+                    hr[i] += xr; hi[i] += xi;
+                }
+            }
+        }
+        std::vector<double> c(2 * n), h(2 * m);
+        for (long long j = 0; j < n; ++j) { c[2 * j] = (double)cr[j]; c[2 * j + 1] = (double)ci[j]; }
+        for (long long j = 0; j < m; ++j) { h[2 * j] = (double)(hr[j] / (long double)m); h[2 * j + 1] = (double)(hi[j] / (long double)m); }
+        blue_chirp[n].ensure(16 * n); blue_hf[n].ensure(16 * m);
+        rt_h2d(blue_chirp[n].p, c.data(), 16 * n, ctx->stream);
+        rt_h2d(blue_hf[n].p, h.data(), 16 * m, ctx->stream);
+        rt_sync(ctx->stream);
     }
 
     // ------------------------------------------------------------------------------------------
@@ -153,6 +256,8 @@ struct FieldEngine : Engine {
         if (const char* e = getenv("MGVIB200_GRAPH")) graphs_on = atoi(e) != 0;
         if (const char* e = getenv("MGVIB200_PF")) use_paired = atoi(e) != 0;
         if (const char* e = getenv("MGVIB200_PERSIST")) persist_on = atoi(e) != 0;
+        if (const char* e = getenv("MGVIB200_BLUE_MIN")) kBlueMinAxis = std::max<long long>(1, atoll(e));
+        if (const char* e = getenv("MGVIB200_BIG_THREADS")) big_block_threads = std::max(32, atoi(e));
         if (const char* e = getenv("MGVIB200_BIG_AP_LGL")) big_ap_lgL = std::min(3, std::max(1, atoi(e)));
         if (const char* e = getenv("MGVIB200_ROW_THREADS")) row_threads = std::max(32, atoi(e));
         if (getenv("MGVIB200_FORCE_GENERIC") && atoi(getenv("MGVIB200_FORCE_GENERIC"))) big = false;
@@ -183,43 +288,9 @@ struct FieldEngine : Engine {
         for (size_t i = 0; i < lens.size(); ++i) {
             const long long n = lens[i];
             if (fast) {
-                if (tw.count(n)) continue;
-                // per-stage twiddle runs (fft_core.h): for each radix-8 stage with Ns > 1, W^j, W^2j, W^4j, j < Ns
-                std::vector<double> t;
-                const int lg = ilog2(n), lead = lg % 3;
-                for (int lgNs = lead; lgNs < lg; lgNs += 3) {
-                    if (lgNs == 0) continue;
-                    const long long Ns = 1LL << lgNs;
-                    for (int e = 1; e <= 4; e *= 2)
-                        for (long long j = 0; j < Ns; ++j) {
-                            long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)(e * j) /
-                                            (long double)(8 * Ns);
-                            t.push_back((double)cosl(a));
-                            t.push_back((double)(-sinl(a)));
-                        }
-                }
-                if (t.empty()) { t.push_back(1.0); t.push_back(0.0); }
-                tw[n].ensure(sizeof(double) * t.size());
-                rt_h2d(tw[n].p, t.data(), sizeof(double) * t.size(), ctx->stream);
-                rt_sync(ctx->stream);
-                if (lead == 2 && lg >= 8) {
-                    // paired transforms (fft_core.h: fft_line_post): radix-8 stages Ns = 8, 64, ... (one run W^j each),
-                    // then the final radix-4 stage: exp(-2 pi i j / n), j < n/4
-                    std::vector<double> u;
-                    const long double tp = 2.0L * 3.14159265358979323846264338327950288L;
-                    for (long long Ns = 8; 8 * Ns <= n / 4; Ns *= 8)
-                        for (long long j = 0; j < Ns; ++j) {
-                            const long double a = tp * (long double)j / (long double)(8 * Ns);
-                            u.push_back((double)cosl(a)); u.push_back((double)(-sinl(a)));
-                        }
-                    for (long long j = 0; j < n / 4; ++j) {
-                        const long double a = tp * (long double)j / (long double)n;
-                        u.push_back((double)cosl(a)); u.push_back((double)(-sinl(a)));
-                    }
-                    twp[n].ensure(sizeof(double) * u.size());
-                    rt_h2d(twp[n].p, u.data(), sizeof(double) * u.size(), ctx->stream);
-                    rt_sync(ctx->stream);
-                }
+                build_fft_tables(n);
+            } else if (n > kBlueMinAxis) {
+                build_bluestein_tables(n);
             } else {
                 if (cas.count(n)) continue;
                 std::vector<double> t((size_t)n * n);
@@ -285,7 +356,7 @@ struct FieldEngine : Engine {
         if (KIND != BIG_A && lg_len - 3 + lgL > 10) throw RtError{"1-D field too long for the four-step path", 3};
         B.lgL = lgL;
         const long long upt = 1LL << (lg_len - 3 + lgL);
-        long long G = std::max<long long>(1, 256 / upt);
+        long long G = std::max<long long>(1, big_block_threads / upt);
         B.units_per_pair = (KIND == BIG_A) ? ((1LL << lg_n2) >> lgL) : ((KIND == BIG_AP) ? ((1LL << lg_n2) >> lgL) : ((1LL << lg_n1) >> 1));
         G = std::min(G, B.units_per_pair);
         G = std::max<long long>(G, (32 + upt - 1) / upt);
@@ -476,8 +547,31 @@ struct FieldEngine : Engine {
     // ------------------------------------------------------------------------------------------
     // generic (any length) chain pieces
     // ------------------------------------------------------------------------------------------
-    void naive_transform_all(double*& cur, double*& other, int nvec, const double* w_after) {
+    void naive_transform_all(double*& cur, double*& other, int nvec, const double* w_after, const int* active = nullptr) {
         for (int a = 0; a < ndim; ++a) {
+            if (dims[a] > kBlueMinAxis) {
+                BlueParams B;
+                memset(&B, 0, sizeof B);
+                const long long n = dims[a];
+                B.in = cur; B.out = other; B.w = (a == ndim - 1) ? w_after : nullptr;
+                B.chirp = blue_chirp.at(n).as<double2>(); B.hf = blue_hf.at(n).as<double2>();
+                B.lg_m = blue_lg_m(n);
+                B.tw = tw.at(1LL << B.lg_m).as<double2>();
+                B.N = N; B.n = (int)n; B.nlines = (long long)nvec * (N / n);
+                B.lines_per_vec = N / n; B.active = active;
+                B.inner = 1;
+                for (int i = a + 1; i < ndim; ++i) B.inner *= dims[i];
+                const int threads = 1 << (B.lg_m - 3);
+                const size_t smem = kSmemHeader + ((size_t)16 << B.lg_m);
+                const long long grid = (B.nlines + 1) / 2;
+                ctx->prof_pre(6000 + a);
+                if (threads <= 256) rt_launch(k_bluestein_axis<256>, grid, threads, smem, ctx->stream, B);
+                else rt_launch(k_bluestein_axis<1024>, grid, threads, smem, ctx->stream, B);
+                ctx->prof_post();
+                ctx->launches++;
+                std::swap(cur, other);
+                continue;
+            }
             NaiveParams Q;
             Q.in = cur; Q.out = other; Q.cas = cas.at(dims[a]).as<double>();
             Q.w = (a == ndim - 1) ? w_after : nullptr;
@@ -511,8 +605,9 @@ struct FieldEngine : Engine {
             rt_launch(k_elem_pro<PRO>, grid, 256, 512, ctx->stream, E);
             ctx->launches++;
         }
-        naive_transform_all(cur, other, nvec, metric ? P.w : nullptr);
-        if (metric) naive_transform_all(cur, other, nvec, nullptr);
+        const int* act = P.mask_active ? P.cg.active : nullptr;
+        naive_transform_all(cur, other, nvec, metric ? P.w : nullptr, act);
+        if (metric) naive_transform_all(cur, other, nvec, nullptr, act);
         {
             ElemParams E;
             E.f = P; E.tmp = cur; E.total = (long long)nvec * N;
@@ -779,7 +874,9 @@ struct FieldEngine : Engine {
             if (it < itmax && sample_cg_persistent(sc, R, nvec, itmax - 1)) it = itmax;
             const bool use_graph = rt_has_graphs && graphs_on && !ctx->profile && it < itmax;
             if (use_graph) {
-                const CgGraphKey key{R, ws_r.p, ws_p.p, ws_t.p, ws_tile.p, w_tiled.p, nvec, o.abstol, o.reltol, itmax};
+                // (the first, host-launched iteration above has already sized every buffer for this nvec)
+                const CgGraphKey key{R, ws_r.p, ws_p.p, ws_t.p, ws_tile.p, w_tiled.p, tmpA.p, tmpB.p, cs.p,
+                                     rws.partials.p, rws.counters.p, nvec, o.abstol, o.reltol, itmax};
                 if (!cg_graph_valid || !(key == cg_graph_key)) {
                     if (cg_graph_valid) { rt_graph_destroy(cg_graph); cg_graph_valid = false; }
                     const int64_t l0 = ctx->launches;

@@ -832,4 +832,82 @@ SIMT_DEVICE void naive_axis_body(const NaiveParams& P, unsigned char*) {
     P.out[idx] = a;
 }
 
+// ------------------------------------------------------------------------------------------
+// Any-length Hartley pass in O(m log m): Bluestein's chirp-z on top of the power-of-two FFT core.
+//   Z[k] = sum_j z_j e^(-2 pi i j k / n),  j k = (j^2 + k^2 - (k - j)^2) / 2
+//        = c_k * sum_j (z_j c_j) conj(c_(k-j)),        c_j = e^(-i pi j^2 / n)
+// i.e. a cyclic convolution of length m >= 2n - 1 (m a power of two) of y_j = z_j c_j with the wrapped chirp
+// h_j = conj(c_|j|): two length-m FFTs per complex line (the inverse one as conj(FFT(conj(.)))), the FFT of h
+// precomputed (scaled by 1/m).  As everywhere a complex line packs TWO real lines z = a + i b and the Hartley
+// pair comes out of Z[k], Z[n-k]; the result is 2 H(.) like the direct pass it replaces (naive_axis_body).
+// One block = one pair of neighbouring lines, m/8 threads.
+// ------------------------------------------------------------------------------------------
+struct BlueParams {
+    const double* in; double* out;
+    const double* w;            // optional pointwise weight on the output (N), or null
+    const double2* chirp;       // c_j, j < n
+    const double2* hf;          // FFT_m(h) / m
+    const double2* tw;          // per-stage twiddles of the length-m FFT (fft_core.h layout)
+    long long N, inner, nlines; // nlines = nvec * N / n real lines
+    long long lines_per_vec;    // N / n
+    const int* active;          // CG iterations: per-vector active flags (a converged vector's stale line must not
+                                // share a complex transform with a live one: its magnitude drifts away and the
+                                // rounding of the partner is relative to the larger of the two), or null
+    int n, lg_m;
+};
+
+SIMT_DEVICE void bluestein_axis_body(const BlueParams& P, unsigned char* smem_raw) {
+    const int lt = SIMT_TID;
+    const int m8 = 1 << (P.lg_m - 3);
+    LineView lv;
+    lv.sm = reinterpret_cast<double2*>(smem_raw + kSmemHeader);
+    lv.lgL = 0;
+    lv.l = 0;
+    const long long la = 2 * SIMT_BID, lb = la + 1;
+    bool va = true, vb = lb < P.nlines;
+    if (P.active) {
+        va = P.active[la / P.lines_per_vec] != 0;
+        vb = vb && P.active[lb / P.lines_per_vec] != 0;
+        if (!va && !vb) return;                  // uniform for the block
+    }
+    const long long ni = (long long)P.n * P.inner;
+    const long long base_a = (la / P.inner) * ni + (la % P.inner);
+    const long long base_b = vb ? (lb / P.inner) * ni + (lb % P.inner) : base_a;
+    double2 v[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int j = lt + t * m8;
+        if (j < P.n) {
+            const double a = va ? P.in[base_a + (long long)j * P.inner] : 0.0;
+            const double b = vb ? P.in[base_b + (long long)j * P.inner] : 0.0;
+            v[t] = cmul(make_double2(a, b), SIMT_LDG(P.chirp + j));
+        } else {
+            v[t] = make_double2(0.0, 0.0);
+        }
+    }
+    fft_line_forward<0>(v, lv, lt, P.lg_m, P.tw);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const double2 x = cmul(v[t], SIMT_LDG(P.hf + lt + t * m8));
+        v[t] = make_double2(x.x, -x.y);
+    }
+    fft_line_forward<0>(v, lv, lt, P.lg_m, P.tw);
+    // shared memory now holds conj(convolution) in natural order; Z[k] = c_k * conj(.)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int k = lt + t * m8;
+        if (k < P.n) {
+            const int kp = k ? P.n - k : 0;
+            const double2 zk = cmul(SIMT_LDG(P.chirp + k), make_double2(v[t].x, -v[t].y));
+            const double2 sp = lv.raw(kp);
+            const double2 zn = cmul(SIMT_LDG(P.chirp + kp), make_double2(sp.x, -sp.y));
+            double oa = zk.x - zk.y + zn.x + zn.y, ob = zk.x + zk.y + zn.y - zn.x;
+            const long long pa = base_a + (long long)k * P.inner, pb = base_b + (long long)k * P.inner;
+            if (P.w) { oa *= SIMT_LDG(P.w + pa % P.N); if (vb) ob *= SIMT_LDG(P.w + pb % P.N); }
+            if (va) P.out[pa] = oa;
+            if (vb) P.out[pb] = ob;
+        }
+    }
+}
+
 }  // namespace mgvi

@@ -12,7 +12,12 @@ SIMT_GLOBAL(256) k_vec(SIMT_KARGS(VecParams)) {
 }
 
 static const int kVecThreads = 256;
-static const long long kVecPerBlock = 4096;
+static long long vec_per_block() {
+    static long long v = 0;
+    if (!v) { const char* e = getenv("MGVIB200_VEC_PER_BLOCK"); v = (e && atoll(e) >= 256) ? (atoll(e) & ~1LL) : 4096; }
+    return v;
+}
+#define kVecPerBlock (vec_per_block())
 
 void reduce_ws_ensure(ReduceWs& ws, mgvib200_ctx* ctx, size_t npartials, size_t ncounters) {
     ws.partials.ensure(sizeof(double) * npartials);

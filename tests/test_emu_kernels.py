@@ -290,6 +290,53 @@ def _random_shapes(seed, count):
     return out
 
 
+@pytest.mark.parametrize("dims,like", [((40,), "LIKE_NORMAL"), ((100,), "LIKE_POISSON"), ((33,), "LIKE_POISSON"),
+                                       ((129,), "LIKE_NORMAL"), ((257,), "LIKE_POISSON"), ((1000,), "LIKE_POISSON"),
+                                       ((12, 40), "LIKE_POISSON"), ((36, 8), "LIKE_NORMAL"), ((5, 50), "LIKE_POISSON"),
+                                       ((2, 35, 34), "LIKE_NORMAL"), ((64, 100), "LIKE_POISSON")])
+def test_any_length_axes_bluestein(pkg, emu_ctx, dims, like):
+    """Axes that are not a power of two and longer than 32 points take the O(m log m) Bluestein pass
+    (field_pass.h: bluestein_axis_body) -- odd and even lengths, lengths next to a power of two, an odd number
+    of lines (the unpaired last line), mixed with short direct-pass axes and with power-of-two axes."""
+    from helpers import TIGHT_O
+    cfg = _field(pkg, dims, like, 3)
+    m = pkg.model_from_config(cfg, emu_ctx)
+    om = oracle_model(cfg)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(**TIGHT), emu_ctx)
+    V = np.random.default_rng(4).standard_normal((m.n_theta, 3))
+    lin = om.linearize(cfg["center"])
+    MVo = np.stack([O.metric_apply(lin, V[:, i]) for i in range(3)], axis=1)
+    assert rel(s.metric_apply(V), MVo) < 1e-12, dims
+    if m.n_theta > 1100:        # the emulator runs one fiber per thread: CG solves only on the small shapes
+        m.close()
+        return
+    R = pkg.sample_residuals(s, 3, draws=(cfg["Z1"], cfg["Z2"]))
+    Ro, _, _ = O.sample_residuals_cg(om, cfg["center"], cfg["Z1"], cfg["Z2"], **TIGHT_O)
+    assert rel(R, Ro) < RTOL, dims
+    f, g = pkg.kl_value_grad(m, cfg["center"], Ro)
+    assert abs(f - O.mean_neg_log_pstr(om, Ro, cfg["center"])) < 1e-12 * abs(f)
+    assert rel(g, O.kl_gradient(om, Ro, cfg["center"])) < RTOL
+    m.close()
+
+
+def test_bluestein_converged_partner_is_masked(pkg, emu_ctx):
+    """Two residual samples of a 1-D any-length field share one complex transform.  Once one of them has
+    converged its line must leave the transform (a stale line is transformed over and over, grows by ~1e6 per
+    iteration and swamps the rounding of its live partner -- found on the GPU as NaN residuals)."""
+    cfg = _field(pkg, (100,), "LIKE_POISSON", 2)
+    Z1, Z2 = cfg["Z1"].copy(), cfg["Z2"].copy()
+    Z1[:, 1] *= 1e-9
+    Z2[:, 1] *= 1e-9
+    m = pkg.model_from_config(cfg, emu_ctx)
+    om = oracle_model(cfg)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(abstol=1e-10, reltol=1e-12), emu_ctx)
+    R, info = pkg.sample_residuals(s, 2, draws=(Z1, Z2), return_info=True)
+    Ro, ito, _ = O.sample_residuals_cg(om, cfg["center"], Z1, Z2, atol=1e-10, rtol=1e-12)
+    assert info["iters"][1] + 10 < info["iters"][0], info["iters"]
+    assert rel(R[:, 0], Ro[:, 0]) < RTOL and np.linalg.norm(R[:, 1] - Ro[:, 1]) < 1e-9 * np.linalg.norm(Ro[:, 0])
+    m.close()
+
+
 @pytest.mark.parametrize("dims", _random_shapes(2026, 24))
 def test_metric_random_shapes(pkg, emu_ctx, dims):
     """Seeded random shapes mixing power-of-two (fast kernels) and other axis lengths (generic

@@ -172,6 +172,22 @@ def test_large_2d_shapes(pkg, gpu_ctx, dims, like):
     _full_metric_checks(pkg, gpu_ctx, cfg, 1)
 
 
+@pytest.mark.parametrize("dims,like", [((1000,), "LIKE_POISSON"), ((4095,), "LIKE_NORMAL"), ((1000, 1000), "LIKE_POISSON"),
+                                       ((1536, 640), "LIKE_NORMAL"), ((100, 90, 80), "LIKE_POISSON"), ((3000, 7), "LIKE_NORMAL")])
+def test_any_length_axes(pkg, gpu_ctx, dims, like):
+    """Axis lengths that are not a power of two: the O(m log m) Bluestein pass
+    (field_pass.h: bluestein_axis_body) up to the 4096-point limit, 1-D to 3-D, next to short direct-pass axes."""
+    cfg = _field(pkg, dims, like, 1)
+    _full_metric_checks(pkg, gpu_ctx, cfg, 1)
+
+
+def test_any_length_full_ops_1d_1000(pkg, gpu_ctx):
+    """Every row of the path on a 1000-pixel line and a 96 x 80 field (Bluestein axes), end to end incl. the step."""
+    for dims, like in (((1000,), "LIKE_POISSON"), ((96, 80), "LIKE_NORMAL")):
+        cfg = _field(pkg, dims, like, 4)
+        assert_field_ops(check_field_ops(pkg, gpu_ctx, cfg, check_step=True), cfg)
+
+
 def test_full_size_c5_256cubed(pkg, gpu_ctx):
     cfg = _field(pkg, (256, 256, 256), "LIKE_POISSON", 1)
     _full_metric_checks(pkg, gpu_ctx, cfg, 1)
