@@ -82,12 +82,18 @@ namespace mgvi {
 
 struct CgWs {
     int nvec = 0;
-    DevBuf gamma, alpha, beta, eps, rnorm, pAp, iters, active, n_active;
+    DevBuf gamma, alpha, beta, eps, rnorm, pAp, iters, active, n_active, x_pending, x_count;
+    ~CgWs() {
+        DevBuf* all[] = {&gamma, &alpha, &beta, &eps, &rnorm, &pAp, &iters, &active, &n_active, &x_pending, &x_count};
+        for (auto* b : all) b->release();
+    }
+    bool defer = false;     // hand out the deferred-solution-update flags (sampler CG of 2-D / 3-D fields only)
     CgScalars scalars(double atol, double rtol, long long itmax, int flavor) const {
         CgScalars c;
         c.gamma = gamma.as<double>(); c.alpha = alpha.as<double>(); c.beta = beta.as<double>();
         c.eps = eps.as<double>(); c.rnorm = rnorm.as<double>(); c.pAp = pAp.as<double>();
         c.iters = iters.as<int>(); c.active = active.as<int>(); c.n_active = n_active.as<int>();
+        c.x_pending = defer ? x_pending.as<int>() : nullptr; c.x_count = defer ? x_count.as<unsigned>() : nullptr;
         c.atol = atol; c.rtol = rtol; c.itmax = itmax; c.flavor = flavor;
         return c;
     }
@@ -95,7 +101,7 @@ struct CgWs {
         if (n <= nvec) return;
         size_t d = sizeof(double) * n, i = sizeof(int) * n;
         gamma.ensure(d); alpha.ensure(d); beta.ensure(d); eps.ensure(d); rnorm.ensure(d); pAp.ensure(d);
-        iters.ensure(i); active.ensure(i); n_active.ensure(sizeof(int) * 4);
+        iters.ensure(i); active.ensure(i); n_active.ensure(sizeof(int) * 4); x_pending.ensure(i); x_count.ensure(i);
         nvec = n;
     }
 };
@@ -179,6 +185,9 @@ void vec_cg_init(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, const dou
                  double* r, double* p, long long N, int nvec);
 void vec_cg_update(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* x, double* r, const double* p,
                    const double* Ap, long long N, int nvec);
+// deferred solution update (field_pass.h: defer_x): the residual half of the update; the flush of what is still pending
+void vec_cg_update_r(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* r, const double* Ap, long long N, int nvec);
+void vec_x_flush(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* x, const double* p, long long N, int nvec);
 // the same update as kernel parameters + block count, for kernels that run it as one of their phases
 VecParams vec_cg_update_params(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* x, double* r,
                                const double* p, const double* Ap, long long N, int nvec, long long* grid);

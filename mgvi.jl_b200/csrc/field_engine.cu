@@ -69,6 +69,12 @@ struct FieldEngine : Engine {
     ReduceWs rws;
     CgWs cgws, ncgws;
     DevBuf ws_r, ws_p, ws_t;          // sampler CG vectors [nvec][N]
+    DevBuf ws_p2;                     // second p buffer of the deferred solution update (field_pass.h: defer_x)
+    // MGVIB200_DEFER_X=0: keep x += alpha p in the streaming update kernel.  Default on for 2-D / 3-D fields:
+    // the 24 N bytes of the solution update ride in the fused axis-0 pass of the next iteration
+    bool defer_force = false;
+    int defer_mode = 1;               // 1: before the transforms of the block; 2: after them, operands prefetched into L2 at block start
+    bool defer_on = true;
     DevBuf pt_t;                      // per-point scratch [npoints][N]
     DevBuf gather, sc_gather, kl_red; // canonical sums: gathered chunk partials [chunks][N], per-point scalars
     DevBuf qsum;                      // N
@@ -81,12 +87,12 @@ struct FieldEngine : Engine {
         // every buffer a captured kernel may point into: the CG vectors, the pass scratch, the staging buffers of
         // the generic and four-step paths and the reduction workspace (all of them can be re-allocated larger by a
         // later call with more vectors, e.g. a KL evaluation over 2n points)
-        const void *R, *r, *p, *t, *tile, *wt, *ta, *tb, *cs, *part, *cnt;
+        const void *R, *r, *p, *p2, *t, *tile, *wt, *ta, *tb, *cs, *part, *cnt;
         int nvec;
         double atol, rtol;
         long long itmax;
         bool operator==(const CgGraphKey& o) const {
-            return R == o.R && r == o.r && p == o.p && t == o.t && tile == o.tile && wt == o.wt && ta == o.ta &&
+            return R == o.R && r == o.r && p == o.p && p2 == o.p2 && t == o.t && tile == o.tile && wt == o.wt && ta == o.ta &&
                    tb == o.tb && cs == o.cs && part == o.part && cnt == o.cnt && nvec == o.nvec &&
                    atol == o.atol && rtol == o.rtol && itmax == o.itmax;
         }
@@ -113,7 +119,7 @@ struct FieldEngine : Engine {
         if (cg_graph_valid) rt_graph_destroy(cg_graph);
         dense_chol_destroy(chol);
         Mdense.release(); eye.release();
-        DevBuf* all[] = {&A, &data, &w, &q, &wbar, &center, &w_tiled, &ws_tile, &ws_r, &ws_p, &ws_t, &pt_t, &gather, &sc_gather, &kl_red, &qsum, &n_x, &n_r,
+        DevBuf* all[] = {&A, &data, &w, &q, &wbar, &center, &w_tiled, &ws_tile, &ws_r, &ws_p, &ws_p2, &ws_t, &pt_t, &gather, &sc_gather, &kl_red, &qsum, &n_x, &n_r,
                          &n_p, &n_t, &tmpA, &tmpB, &pbar, &pparams, &cs, &tlo, &thi, &data_perm, &rws.partials, &rws.counters, &rws.red};
         for (auto* b : all) b->release();
         for (auto& kv : tw) kv.second.release();
@@ -256,6 +262,7 @@ struct FieldEngine : Engine {
         if (const char* e = getenv("MGVIB200_GRAPH")) graphs_on = atoi(e) != 0;
         if (const char* e = getenv("MGVIB200_PF")) use_paired = atoi(e) != 0;
         if (const char* e = getenv("MGVIB200_PERSIST")) persist_on = atoi(e) != 0;
+        if (const char* e = getenv("MGVIB200_DEFER_X")) { defer_on = atoi(e) != 0; defer_force = defer_on; if (atoi(e) > 0) defer_mode = std::min(2, atoi(e)); }
         if (const char* e = getenv("MGVIB200_BLUE_MIN")) kBlueMinAxis = std::max<long long>(1, atoll(e));
         if (const char* e = getenv("MGVIB200_BIG_THREADS")) big_block_threads = std::max(32, atoi(e));
         if (const char* e = getenv("MGVIB200_BIG_AP_LGL")) big_ap_lgL = std::min(3, std::max(1, atoi(e)));
@@ -832,6 +839,17 @@ struct FieldEngine : Engine {
         ws_r.ensure(vb); ws_p.ensure(vb); ws_t.ensure(vb);
         cgws.ensure(nvec);
         const long long itmax = o.maxiters > 0 ? o.maxiters : N;
+        // deferred solution update: 2-D / 3-D fast path only (the fused axis-0 pass carries it)
+        // Measured (profiles/README.md, round 2): C3 (2048-point axis 0) 3.50 -> 3.36 ms per iteration; C5 (256-point
+        // axis 0, a pass that is already close to its HBM time) 4.30 -> 4.34 ms: on by default for 2-D fields with a long
+        // axis 0 only (MGVIB200_DEFER_X=1/2 forces it on wherever it applies, =0 off)
+        const bool defer = (defer_force || (defer_on && ndim == 2 && dims[0] >= 1024)) && fast && !big && ndim >= 2 && (N & 1) == 0;
+        cgws.defer = defer;
+        if (defer) {
+            ws_p2.ensure(vb);
+            rt_memset(cgws.x_pending.p, 0, sizeof(int) * nvec, ctx->stream);
+            rt_memset(cgws.x_count.p, 0, sizeof(int) * nvec, ctx->stream);
+        }
         CgScalars sc = cgws.scalars(o.abstol, o.reltol, itmax, CG_KRYLOV);
         rt_memset(cgws.n_active.p, 0, sizeof(int) * 4, ctx->stream);
         rt_event_record(ctx->ev0, ctx->stream);
@@ -855,34 +873,44 @@ struct FieldEngine : Engine {
         h[0] = 1;
         rt_d2h(h, cgws.n_active.p, sizeof(int), ctx->stream);
         rt_sync(ctx->stream);
-        auto launch_iter = [&](bool first) {
+        // `k` = index of the lock-step iteration.  Deferred mode: p_k lives in buffer k % 2 (the first pass reads
+        // p_(k-1) from the other one), the fused axis-0 pass applies x += alpha_(k-1) p_(k-1), the update kernel
+        // only touches r
+        double* pbuf[2] = {ws_p.as<double>(), defer ? ws_p2.as<double>() : ws_p.as<double>()};
+        auto launch_iter = [&](bool first, long long k) {
             FieldPassParams P = base_params();
-            P.r = ws_r.as<double>(); P.p = ws_p.as<double>();
-            P.vin = ws_p.as<double>(); P.vin_ld = N;
+            double* p_cur = pbuf[k & 1];
+            double* p_prev = pbuf[(k & 1) ^ 1];
+            P.r = ws_r.as<double>();
+            P.p = first ? p_cur : p_prev;
+            P.p_out = defer ? p_cur : nullptr;
+            P.vin = p_cur; P.vin_ld = N;
             P.out = ws_t.as<double>(); P.out_ld = N;
             P.w = w.as<double>();
             P.first_iter = first ? 1 : 0;
             P.cg = sc;
             P.mask_active = 1;
+            if (defer) { P.defer_x = defer_mode; P.x_prev_p = p_prev; P.xout = R; }
             chain_metric<PRO_CG>(P, nvec, ws_t.as<double>(), FIN_CG_PAP, nullptr);
-            vec_cg_update(ctx, rws, sc, R, ws_r.as<double>(), ws_p.as<double>(), ws_t.as<double>(), N, nvec);
+            if (defer) vec_cg_update_r(ctx, rws, sc, ws_r.as<double>(), ws_t.as<double>(), N, nvec);
+            else vec_cg_update(ctx, rws, sc, R, ws_r.as<double>(), ws_p.as<double>(), ws_t.as<double>(), N, nvec);
         };
         long long it = 0;
         if (h[0] > 0 && itmax > 0) {
-            launch_iter(true);
+            launch_iter(true, 0);
             it = 1;
             if (it < itmax && sample_cg_persistent(sc, R, nvec, itmax - 1)) it = itmax;
             const bool use_graph = rt_has_graphs && graphs_on && !ctx->profile && it < itmax;
             if (use_graph) {
                 // (the first, host-launched iteration above has already sized every buffer for this nvec)
-                const CgGraphKey key{R, ws_r.p, ws_p.p, ws_t.p, ws_tile.p, w_tiled.p, tmpA.p, tmpB.p, cs.p,
+                const CgGraphKey key{R, ws_r.p, ws_p.p, defer ? ws_p2.p : nullptr, ws_t.p, ws_tile.p, w_tiled.p, tmpA.p, tmpB.p, cs.p,
                                      rws.partials.p, rws.counters.p, nvec, o.abstol, o.reltol, itmax};
                 if (!cg_graph_valid || !(key == cg_graph_key)) {
                     if (cg_graph_valid) { rt_graph_destroy(cg_graph); cg_graph_valid = false; }
                     const int64_t l0 = ctx->launches;
                     rt_capture_begin(ctx->stream);
                     try {
-                        for (int k = 0; k < kCgChunk; ++k) launch_iter(false);
+                        for (int k = 0; k < kCgChunk; ++k) launch_iter(false, 1 + k);     // replays start at odd k: same buffer parity
                         cg_graph = rt_capture_end(ctx->stream);
                     } catch (...) {
                         rt_capture_abort(ctx->stream);
@@ -901,7 +929,7 @@ struct FieldEngine : Engine {
                 // 1, 2, 4, 8, 8, ... iterations
                 int poll = 1;
                 while (h[0] > 0 && it < itmax) {
-                    for (int k = 0; k < poll && it < itmax; ++k, ++it) launch_iter(false);
+                    for (int k = 0; k < poll && it < itmax; ++k, ++it) launch_iter(false, it);
                     rt_d2h(h, cgws.n_active.p, sizeof(int), ctx->stream);
                     rt_sync(ctx->stream);
                     if (poll < kCgChunk) poll *= 2;
@@ -926,6 +954,9 @@ struct FieldEngine : Engine {
                 }
             }
         }
+        // deferred mode: vectors that stopped in the very last launched update still lack its alpha p
+        // (`it` iterations were launched; the last one built p in buffer (it - 1) % 2)
+        if (defer && it > 0) vec_x_flush(ctx, rws, sc, R, pbuf[(it - 1) & 1], N, nvec);
         rt_event_record(ctx->ev1, ctx->stream);
         std::vector<int> hi(nvec);
         std::vector<double> hr(nvec);

@@ -38,6 +38,8 @@ struct CgScalars {
     int* iters;
     int* active;       // 1 while the vector still iterates
     int* n_active;     // number of active vectors (single int)
+    int* x_pending;    // deferred solution update (FieldPassParams::defer_x): 1 = x still lacks alpha * p of the last update
+    unsigned* x_count; // ... blocks of the vector that have applied it (self-resetting)
     double atol, rtol;
     long long itmax;
     int flavor;        // CG_KRYLOV (sampler) or CG_ITSOLVERS (Newton inner CG, A.2)
@@ -63,6 +65,14 @@ struct FieldPassParams {
     const double* Z1;  long long Z1_ld, Z1_off, Z1_stride;
     const double* Z2;  long long Z2_ld;
     double* r; double* p; double* xout;       // CG vectors (leading dimension N)
+    double* p_out;                            // PRO_CG: where p = r + beta p is written (null: in place)
+    // Deferred solution update of the sampler CG (2-D / 3-D fields): x += alpha p moves 24 N bytes that need
+    // nothing but alpha, so it rides in the fused axis-0 pass of the NEXT iteration -- a kernel bound by the L1
+    // data pipe with two thirds of its HBM time idle -- instead of the streaming update kernel, which is bound
+    // by HBM.  p is double-buffered (the next first pass writes p = r + beta p elsewhere), x_prev_p is the
+    // previous iteration's p.
+    int defer_x;
+    const double* x_prev_p;
     const double* data;                       // observations (N)
     double* w_out; double* q_out; double* lam_out;   // EPI_LINEARIZE at the centre (out == null)
     double scale, offset, sigma, inv_sigma2;
@@ -147,7 +157,7 @@ SIMT_DEVICE double2 pro_pair(const FieldPassParams& P, int sa, int sb, long long
             double2 rr = ld_pair(P.r, ia, ib, va, vb, adj);
             const double ba = va ? P.cg.beta[sa] : 0.0, bb = vb ? P.cg.beta[sb] : 0.0;
             pp = make_double2(rr.x + ba * pp.x, rr.y + bb * pp.y);
-            st_pair(P.p, ia, ib, va, vb, adj, pp);
+            st_pair(P.p_out ? P.p_out : P.p, ia, ib, va, vb, adj, pp);
         }
         double2 a = ldg_pair(P.A, pa, pb, va, vb, adj);
         return make_double2(a.x * pp.x, a.y * pp.y);
@@ -235,7 +245,7 @@ SIMT_DEVICE void epi_pair(const FieldPassParams& P, int sa, int sb, long long pa
 // (k = lt + m n/8) is d1 = 4 step, stepj = step; the paired arrangement (fft_core.h) is d1 = (jB - jA) * kstride,
 // stepj = 2 step.
 template <bool ADJ>
-SIMT_DEVICE void pro_cg_block(double2 (&v)[8], double* __restrict__ p, const double* __restrict__ r,
+SIMT_DEVICE void pro_cg_block(double2 (&v)[8], const double* __restrict__ p, double* pout, const double* __restrict__ r,
                               const double* __restrict__ A, unsigned off_a, unsigned off_b, int d1, unsigned stepj,
                               long long vec_off, double beta, bool first_iter) {
     // p = r + beta p (skipped on the first iteration, where p = r already) ; v = A . p
@@ -254,7 +264,7 @@ SIMT_DEVICE void pro_cg_block(double2 (&v)[8], double* __restrict__ p, const dou
             for (int j = 0; j < 4; ++j) {
                 const unsigned oa = off_a + h * d1 + j * stepj, ob = off_b + h * d1 + j * stepj;
                 pp[j] = make_double2(rr[j].x + beta * pp[j].x, rr[j].y + beta * pp[j].y);
-                st_pair(p, vec_off + oa, vec_off + ob, true, true, ADJ, pp[j]);
+                st_pair(pout, vec_off + oa, vec_off + ob, true, true, ADJ, pp[j]);
             }
         }
 #pragma unroll
@@ -376,6 +386,7 @@ SIMT_DEVICE void finalize_vec(int fin, const CgScalars& cg, double* red_out, int
             if (act) SIMT_ATOMIC_ADD_I32(cg.n_active, 1);
         }
     } else if (fin == FIN_CG_RR) {
+        if (cg.x_pending) cg.x_pending[s] = 1;       // deferred solution update: x now lacks alpha * p of this update
         const double rn = sqrt(tot);
         cg.rnorm[s] = rn;
         const int it = cg.iters[s] + 1;
@@ -431,6 +442,35 @@ SIMT_HD long long field_pass_smem_bytes_staged(int n, int L, int G) {
     return field_pass_smem_bytes(n, L, G) + (long long)G * 2 * n * 8;
 }
 
+// Deferred solution update, one block's share: the slab [bt, bt + 1) * N / ntb of vector s; all loads of a round
+// first, through __restrict__ pointers.  The last block of the vector to finish clears the flag (every block --
+// and, by the caller's barrier, every thread of it -- has read it by then).
+SIMT_DEVICE void deferred_x_update(const FieldPassParams& P, int s, long long bt, int tid) {
+    const double alpha = P.cg.alpha[s];
+    const long long slab2 = (P.N / P.ntb) >> 1;                 // double2 elements per block
+    const long long o2 = (((long long)s * P.N) >> 1) + bt * slab2;
+    double2* __restrict__ x2 = reinterpret_cast<double2*>(P.xout) + o2;
+    const double2* __restrict__ p2 = reinterpret_cast<const double2*>(P.x_prev_p) + o2;
+    const int nt = SIMT_NTID;
+    for (long long i0 = tid; i0 < slab2; i0 += 4 * nt) {
+        double2 xv[4], pv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + u * nt < slab2) { xv[u] = x2[i0 + u * nt]; pv[u] = p2[i0 + u * nt]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + u * nt < slab2) {
+                xv[u].x += alpha * pv[u].x; xv[u].y += alpha * pv[u].y;
+                x2[i0 + u * nt] = xv[u];
+            }
+    }
+    if (tid == 0) {
+        SIMT_FENCE();
+        const unsigned c = SIMT_ATOMIC_INC_U32(&P.cg.x_count[s]);
+        if (c == (unsigned)(P.ntb - 1)) { P.cg.x_count[s] = 0; P.cg.x_pending[s] = 0; }
+    }
+}
+
 // GEO is a compile-time geometry class:
 //   GEO_CONTIG : lines along the last (contiguous) axis; a unit = two neighbouring rows of one vector
 //   GEO_STRIDED: lines along an outer axis; a unit = a tile of 2L neighbouring columns
@@ -468,7 +508,23 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
     if (pairvec) { bt = SIMT_BID; sgrp = 0; }
     else { bt = SIMT_BID / P.nsgrp; sgrp = (int)(SIMT_BID - bt * P.nsgrp); }
     const bool use_active = (P.mask_active != 0);
-    if (use_active && !pairvec && P.nloop == 1) {
+    int x_pend = 0;
+    if (DOUBLE && GEO == GEO_STRIDED && P.defer_x) {
+        // deferred x += alpha p of the previous update (see FieldPassParams::defer_x).  The vector may have
+        // converged in that update: then this is all the block does.
+        x_pend = P.cg.x_pending[sgrp];              // uniform for the whole block
+        const int act = P.cg.active[sgrp];
+        SIMT_SYNC();        // every thread has read the flags before thread 0 may clear x_pending (deferred_x_update)
+        if (!x_pend && !act) return;
+        if (x_pend && (!act || P.defer_x == 1)) { deferred_x_update(P, sgrp, bt, tid); x_pend = 0; }
+        if (!act) return;
+        // defer_x == 2: the update runs AFTER the transforms of this block; its operands are pulled into L2 now
+        if (x_pend && tid == 0) {
+            const long long slab = P.N / P.ntb, o = (long long)sgrp * P.N + bt * slab;
+            SIMT_PREFETCH_BULK_L2(P.xout + o, (unsigned)(slab * 8));
+            SIMT_PREFETCH_BULK_L2(P.x_prev_p + o, (unsigned)(slab * 8));
+        }
+    } else if (use_active && !pairvec && P.nloop == 1) {
         if (!P.cg.active[sgrp]) return;    // uniform for the whole block
     }
 
@@ -574,10 +630,10 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
         } else if (valid) {
             if (PRO == PRO_CG) {
                 if (PF == 1)
-                    pro_cg_block<GEO == GEO_STRIDED>(v, P.p, P.r, P.A, off_a, off_b, pd1, 2 * step, (long long)sa * P.N,
+                    pro_cg_block<GEO == GEO_STRIDED>(v, P.p, P.p_out ? P.p_out : P.p, P.r, P.A, off_a, off_b, pd1, 2 * step, (long long)sa * P.N,
                                                      P.first_iter ? 0.0 : P.cg.beta[sa], P.first_iter != 0);
                 else
-                    pro_cg_block<GEO == GEO_STRIDED>(v, P.p, P.r, P.A, off_a, off_b, 4 * (int)step, step, (long long)sa * P.N,
+                    pro_cg_block<GEO == GEO_STRIDED>(v, P.p, P.p_out ? P.p_out : P.p, P.r, P.A, off_a, off_b, 4 * (int)step, step, (long long)sa * P.N,
                                                      P.first_iter ? 0.0 : P.cg.beta[sa], P.first_iter != 0);
             } else if (PRO == PRO_LOAD && GEO == GEO_CONTIG && P.t_lg_wt && n8 >= 32) {
                 // tile-major scratch, row pass: a unit's two rows sit wt reals apart, so lane pairs
@@ -722,6 +778,7 @@ SIMT_DEVICE void field_pass_body(const FieldPassParams& P, unsigned char* smem_r
             }
         }
     }
+    if (DOUBLE && GEO == GEO_STRIDED && x_pend) deferred_x_update(P, sgrp, bt, tid);
     // ---- scalar reductions -----------------------------------------------------------------
     if (P.fin == FIN_NONE) return;
     if (P.fin == FIN_TOTAL) {

@@ -152,6 +152,19 @@ void vec_cg_update(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double*
     vec_launch(ctx, ws, P);
 }
 
+void vec_cg_update_r(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* r, const double* Ap, long long N, int nvec) {
+    VecParams P = vp_zero();
+    P.op = VOP_CG_UPDATE_R; P.N = N; P.nvec = nvec; P.r = r; P.Ap = Ap;
+    P.fin = FIN_CG_RR; P.cg = cg;
+    vec_launch(ctx, ws, P);
+}
+
+void vec_x_flush(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* x, const double* p, long long N, int nvec) {
+    VecParams P = vp_zero();
+    P.op = VOP_X_FLUSH; P.N = N; P.nvec = nvec; P.x = x; P.p = p; P.cg = cg;
+    vec_launch(ctx, ws, P);
+}
+
 VecParams vec_cg_update_params(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* x, double* r,
                                const double* p, const double* Ap, long long N, int nvec, long long* grid) {
     VecParams P = vp_zero();

@@ -21,6 +21,8 @@ enum {
     VOP_FLIP = 10,       // out[i, s] = in[N-1-i, s]                            (index reversal)
     VOP_COPY = 11,       // out = in                                            (per vector)
     VOP_TILE = 12,       // out[tile-major i] = in[natural index of i]           (2-D relayout, field_pass.h)
+    VOP_CG_UPDATE_R = 14,// r -= alpha Ap ; acc = r.r   (per vector; the x half is deferred, field_pass.h: defer_x)
+    VOP_X_FLUSH = 15,    // x += alpha p for vectors whose deferred update is still pending  (per vector)
     VOP_SUM_CANON = 13   // out[s] = scale * sum_{c < nsum} ( sum_{j < per} in[(s nsum + c) per + j] )
                          //   two-level sequential sum in the canonical sample order (engine.h: CanonShape)
 };
@@ -48,6 +50,12 @@ SIMT_DEVICE void vec_elem(const VecParams& P, int s, long long i, double alpha, 
             P.r[gi] = rv;
             acc += rv * rv;
         } break;
+        case VOP_CG_UPDATE_R: {
+            const double rv = P.r[gi] - alpha * P.Ap[gi];
+            P.r[gi] = rv;
+            acc += rv * rv;
+        } break;
+        case VOP_X_FLUSH: P.x[gi] += alpha * P.p[gi]; break;
         case VOP_CG_INIT: {
             const double b = P.in[(long long)s * P.in_ld + i];
             P.r[gi] = b;
@@ -101,9 +109,10 @@ SIMT_DEVICE void vec_body(const VecParams& P, unsigned char* smem_raw, long long
     const long long BID = vbid >= 0 ? vbid : SIMT_BID;
     const int s = (int)(BID % P.nvec);
     const long long chunk = BID / P.nvec;
-    const bool cg_op = (P.op == VOP_CG_UPDATE || P.op == VOP_CG_PUPD || P.op == VOP_CG_PAP);
+    const bool cg_op = (P.op == VOP_CG_UPDATE || P.op == VOP_CG_PUPD || P.op == VOP_CG_PAP || P.op == VOP_CG_UPDATE_R);
     if (cg_op && !P.cg.active[s]) return;
-    const double alpha = (P.op == VOP_CG_UPDATE) ? P.cg.alpha[s] : 0.0;
+    if (P.op == VOP_X_FLUSH && !P.cg.x_pending[s]) return;
+    const double alpha = (P.op == VOP_CG_UPDATE || P.op == VOP_CG_UPDATE_R || P.op == VOP_X_FLUSH) ? P.cg.alpha[s] : 0.0;
     const long long lo = chunk * P.per_block;
     long long hi = lo + P.per_block;
     if (hi > P.N) hi = P.N;
@@ -133,6 +142,31 @@ SIMT_DEVICE void vec_body(const VecParams& P, unsigned char* smem_raw, long long
                     xv[u].x += alpha * pv[u].x; xv[u].y += alpha * pv[u].y;
                     rv[u].x -= alpha * av[u].x; rv[u].y -= alpha * av[u].y;
                     x2[i] = xv[u]; r2[i] = rv[u];
+                    acc += rv[u].x * rv[u].x;
+                    acc += rv[u].y * rv[u].y;
+                }
+            }
+        }
+    } else if (P.op == VOP_CG_UPDATE_R && (P.N & 1) == 0) {
+        const long long base = (long long)s * P.N;
+        const double2* __restrict__ a2 = reinterpret_cast<const double2*>(P.Ap + base);
+        double2* __restrict__ r2 = reinterpret_cast<double2*>(P.r + base);
+        // two streams in, one out: eight 16-byte pairs in flight per thread to keep as many bytes outstanding
+        // as the four-stream update does
+        const long long i1 = hi >> 1, nt = SIMT_NTID;
+        for (long long i0 = (lo >> 1) + SIMT_TID; i0 < i1; i0 += 8 * nt) {
+            double2 av[8], rv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const long long i = i0 + u * nt;
+                if (i < i1) { av[u] = a2[i]; rv[u] = r2[i]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const long long i = i0 + u * nt;
+                if (i < i1) {
+                    rv[u].x -= alpha * av[u].x; rv[u].y -= alpha * av[u].y;
+                    r2[i] = rv[u];
                     acc += rv[u].x * rv[u].x;
                     acc += rv[u].y * rv[u].y;
                 }

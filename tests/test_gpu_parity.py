@@ -130,6 +130,33 @@ def test_many_residuals_lockstep_masking(pkg, gpu_ctx):
     m.close()
 
 
+@pytest.mark.parametrize("dims", [(2048, 32), (1024, 256), (64, 32, 16)])
+def test_deferred_solution_update_bitwise(pkg, gpu_ctx, monkeypatch, dims):
+    """x += alpha p inside the fused axis-0 pass of the next iteration (field_pass.h: defer_x; default for 2-D
+    fields with a long axis 0, forced here for the others) against the streaming update kernel: bit for bit,
+    with residuals that converge at different iterations and an iteration cap that stops mid-flight (CUDA-graph
+    replay of 8-iteration chunks included)."""
+    cfg = _field(pkg, dims, "LIKE_NORMAL", 5)
+    scale = np.logspace(-6, 2, 5)
+    Z1, Z2 = cfg["Z1"] * scale, cfg["Z2"] * scale
+    out = {}
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("MGVIB200_DEFER_X", mode)
+        m = pkg.model_from_config(cfg, gpu_ctx)
+        res = []
+        for opts in (dict(abstol=1e-9, reltol=1e-12), dict(abstol=0.0, reltol=0.0, maxiters=1),
+                     dict(abstol=0.0, reltol=0.0, maxiters=13), dict(abstol=1e-3, reltol=0.0, maxiters=40)):
+            s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(**opts), gpu_ctx)
+            R, info = pkg.sample_residuals(s, 5, draws=(Z1, Z2), return_info=True)
+            res.append((R.copy(), info["iters"].copy()))
+        out[mode] = res
+        m.close()
+    for mode in ("1", "2"):
+        for (Ra, ia), (Rb, ib) in zip(out["0"], out[mode]):
+            assert np.array_equal(ia, ib) and np.array_equal(Ra, Rb), mode
+    assert len(set(out["1"][0][1].tolist())) >= 3
+
+
 # ---- BASELINE.json full sizes -------------------------------------------------------------------
 def _full_metric_checks(pkg, gpu_ctx, cfg, n_solve):
     m = pkg.model_from_config(cfg, gpu_ctx)
