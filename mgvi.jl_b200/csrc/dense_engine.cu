@@ -6,7 +6,8 @@
 //   M = J' F J + I  (F = 1/sigma^2)            FP64 tensor-core rank-k update (dmma_gemm.h)
 //   MatrixInversion sampler (src/residual_samplers.jl:95-123): the reference forms inv(M) and its
 //   lower Cholesky factor L_Sigma; here (restated for an upper factor):
-//       Mf = P M P (index reversal) = R' R  (blocked upper Cholesky, trailing updates on DMMA)
+//       Mf = P M P (index reversal) = R' R  (blocked upper Cholesky; every block operation except the 64 x 64
+//                                            diagonal factorisation is a DMMA GEMM, see DenseChol::factorize)
 //       L_Sigma = P R^-1 P   (lower, L_Sigma L_Sigma' = M^-1),   residuals = P R^-1 (P Z)
 //   no explicit inverse of M is formed.
 //   CG sampler and Newton phase work on M directly (k x k GEMM per iteration).
@@ -28,16 +29,15 @@ struct TriParams {
     double* A; long long ld;      // matrix holding the nb x nb diagonal block at (j0, j0)
     double* X; long long ldx;     // right-hand sides / panel
     int j0, nb, ncols, c0, mode, n;
+    double* Dinv;                 // TRI_POTRF: where the inverse of the factored diagonal block goes (kNb x kNb, column-major)
 };
-enum { TRI_POTRF = 0, TRI_PANEL = 1, TRI_BACK = 2, TRI_SYM = 3, TRI_EYE = 4 };
+enum { TRI_POTRF = 0, TRI_SYM = 3, TRI_EYE = 4 };
 
 // TRI_POTRF: upper Cholesky of the diagonal block in place (one block of 256 threads).
-// TRI_PANEL: X = R_jj^-T A_panel for columns c0.. of block row j0 (thread per column), in place.
-// TRI_BACK : Y = R_jj^-1 W for rows j0..j0+nb of X (thread per column), in place.
 // TRI_SYM  : mirror the upper triangle into the lower one.   TRI_EYE: A = identity.
 //
-// All three block kernels work on a full kNb x kNb block held in registers; a short last block
-// (nb < kNb) is padded with the identity, which the factorisation and both solves leave alone.
+// The diagonal kernel works on a full kNb x kNb block held in registers; a short last block (nb < kNb) is
+// padded with the identity, which the factorisation and the inversion leave alone.
 SIMT_DEVICE void tri_fill_body(const TriParams& P) {
     const long long total = (long long)P.n * P.n;
     const int tid = SIMT_TID, nt = SIMT_NTID;
@@ -94,44 +94,18 @@ SIMT_DEVICE void potrf_body(const TriParams& P, unsigned char* smem) {
         const int r = idx % kNb, c = idx / kNb;
         if (r < P.nb && c < P.nb) P.A[(P.j0 + r) + (long long)(P.j0 + c) * P.ld] = S[r * lds + c];
     }
-}
-
-// Triangular solves with the diagonal block, one right-hand-side column per thread held in 64
-// registers (right-looking substitution: every update of a step is independent, so the FP64 pipe
-// sees 63, 62, ... independent FMAs instead of one dependent chain per row).
-static const int kTriCols = 64;       // columns (threads) per block of the solve kernel
-SIMT_DEVICE void trsolve_body(const TriParams& P, unsigned char* smem) {
-    constexpr int lds = kNb + 1;
-    double* S = reinterpret_cast<double*>(smem);          // [kNb][kNb + 1]
-    double* T = S + kNb * lds;                            // [kNb][kTriCols] staging of the column tile
-    const int tid = SIMT_TID, nt = SIMT_NTID;
-    tri_load_diag(P, S, lds);
-    const long long cbase = P.c0 + SIMT_BID * (long long)kTriCols;
-    const long long cend = (long long)P.c0 + P.ncols;
-    for (int idx = tid; idx < kNb * kTriCols; idx += nt) {
-        const int i = idx % kNb, c = idx / kNb;
-        T[i * kTriCols + c] = (i < P.nb && cbase + c < cend) ? P.X[(P.j0 + i) + (cbase + c) * P.ldx] : 0.0;
-    }
-    SIMT_SYNC();
-    // reciprocal of the diagonal once (64 parallel divisions) instead of a divide on the critical path
-    // of every substitution step
-    double* dinv = T + kNb * kTriCols;
+    if (!P.Dinv) return;
+    // inverse of the diagonal block, X = R^-1 (upper triangular): thread c < 64 solves R x = e_c by right-looking
+    // back substitution in 64 registers.  With it the panel solve R_jj^-T A_panel and the block steps of the
+    // triangular solves are plain GEMMs on the tensor pipe (the usual GPU formulation of trsm); the padded
+    // identity of a short last block inverts to itself.
+    double* dinv = rowbuf;                                // [kNb] reciprocal diagonal
     if (tid < kNb) dinv[tid] = 1.0 / S[tid * lds + tid];
-    double t[kNb];
-#pragma unroll
-    for (int i = 0; i < kNb; ++i) t[i] = T[i * kTriCols + tid];
     SIMT_SYNC();
-    if (P.mode == TRI_PANEL) {
-        // R' x = a:  x_i = a_i / R[i][i], then a_l -= R[i][l] x_i for l > i
+    double t[kNb];
+    if (tid < kNb) {
 #pragma unroll
-        for (int i = 0; i < kNb; ++i) {
-            const double x = t[i] * dinv[i];
-            t[i] = x;
-#pragma unroll
-            for (int l = i + 1; l < kNb; ++l) t[l] -= S[i * lds + l] * x;
-        }
-    } else {
-        // R y = w:  y_i = w_i / R[i][i] from the bottom, then w_l -= R[l][i] y_i for l < i
+        for (int i = 0; i < kNb; ++i) t[i] = (i == tid) ? 1.0 : 0.0;
 #pragma unroll
         for (int i = kNb - 1; i >= 0; --i) {
             const double y = t[i] * dinv[i];
@@ -140,30 +114,32 @@ SIMT_DEVICE void trsolve_body(const TriParams& P, unsigned char* smem) {
             for (int l = 0; l < i; ++l) t[l] -= S[l * lds + i] * y;
         }
     }
+    SIMT_SYNC();                                          // everyone is done reading S
+    if (tid < kNb) {
 #pragma unroll
-    for (int i = 0; i < kNb; ++i) T[i * kTriCols + tid] = t[i];
+        for (int i = 0; i < kNb; ++i) S[i * lds + tid] = t[i];
+    }
     SIMT_SYNC();
-    for (int idx = tid; idx < kNb * kTriCols; idx += nt) {
-        const int i = idx % kNb, c = idx / kNb;
-        if (i < P.nb && cbase + c < cend) P.X[(P.j0 + i) + (cbase + c) * P.ldx] = T[i * kTriCols + c];
+    for (int idx = tid; idx < kNb * kNb; idx += SIMT_NTID) {
+        const int r = idx % kNb, c = idx / kNb;
+        P.Dinv[r + c * kNb] = S[r * lds + c];
     }
 }
 
 SIMT_GLOBAL(128) k_tri_fill(SIMT_KARGS(TriParams)) { SIMT_SMEM_DECL (void)simt_smem; tri_fill_body(P); }
 SIMT_GLOBAL(256) k_potrf(SIMT_KARGS(TriParams)) { SIMT_SMEM_DECL potrf_body(P, simt_smem); }
-SIMT_GLOBAL(64) k_trsolve(SIMT_KARGS(TriParams)) { SIMT_SMEM_DECL trsolve_body(P, simt_smem); }
 
 // MatrixInversion sampler (src/residual_samplers.jl:95-123) on a materialised symmetric metric M (k x k,
 // device memory): shared by the dense-linear engine and by the field engines' small-model dense path.
 struct DenseChol {
     mgvib200_ctx* ctx = nullptr;
     long long k = 0;
-    DevBuf Mf, W, Rinv;
+    DevBuf Mf, W, Rinv, Dinv;      // Dinv: inverses of the diagonal blocks of R, [nblk][kNb x kNb]
     ReduceWs rws;
     bool have_chol = false;
 
     void release() {
-        DevBuf* all[] = {&Mf, &W, &Rinv, &rws.partials, &rws.counters, &rws.red};
+        DevBuf* all[] = {&Mf, &W, &Rinv, &Dinv, &rws.partials, &rws.counters, &rws.red};
         for (auto* b : all) b->release();
         have_chol = false;
     }
@@ -184,18 +160,16 @@ struct DenseChol {
         ctx->launches++;
     }
 
-    void tri(int mode, double* A, long long ld, double* X, long long ldx, int j0, int nb, int c0, int ncols, int n) {
+    void tri(int mode, double* A, long long ld, double* X, long long ldx, int j0, int nb, int c0, int ncols, int n,
+             double* dinv = nullptr) {
         TriParams t;
         t.A = A; t.ld = ld; t.X = X; t.ldx = ldx; t.j0 = j0; t.nb = nb; t.c0 = c0; t.ncols = ncols; t.mode = mode; t.n = n;
-        if ((mode == TRI_PANEL || mode == TRI_BACK) && ncols <= 0) return;
+        t.Dinv = dinv;
         ctx->prof_pre(3100 + mode);
         if (mode == TRI_SYM || mode == TRI_EYE) {
             rt_launch(k_tri_fill, std::min<long long>(((long long)n * n + 127) / 128, 4096), 128, 0, ctx->stream, t);
-        } else if (mode == TRI_POTRF) {
-            rt_launch(k_potrf, 1, 256, sizeof(double) * ((size_t)kNb * (kNb + 1) + 2 * kNb), ctx->stream, t);
         } else {
-            rt_launch(k_trsolve, (ncols + kTriCols - 1) / kTriCols, kTriCols,
-                      sizeof(double) * ((size_t)kNb * (kNb + 1) + (size_t)kNb * kTriCols + kNb), ctx->stream, t);
+            rt_launch(k_potrf, 1, 256, sizeof(double) * ((size_t)kNb * (kNb + 1) + 2 * kNb), ctx->stream, t);
         }
         ctx->prof_post();
         ctx->launches++;
@@ -208,39 +182,70 @@ struct DenseChol {
         return P;
     }
 
-    // Mf = P M P = R'R, R upper, blocked right-looking; the factor stays in Mf (upper triangle)
+    static const int kOuter = 256;    // columns per outer panel: the big trailing updates run with K = 256
+
+    // Mf = P M P = R'R, R upper; the factor stays in Mf (upper triangle), inv(R_jj) of every 64 x 64 diagonal
+    // block in Dinv.  Two-level right-looking: inside an outer panel of 256 columns each 64-block is factored
+    // (one CTA, emits its inverse), its block row becomes X_j = inv(R_jj)' A[j, :] by ONE GEMM over all columns
+    // to the right, and only the remaining rows of the panel are updated (K = 64, at most 192 rows); the rest of
+    // the matrix gets one rank-256 update per panel -- 16 large DMMA launches at n = 4096 instead of 63 rank-64
+    // ones, no thread-per-column substitution kernels on the critical path.
     void factorize(const double* M) {
         if (have_chol) return;
         Mf.ensure(8 * k * k);
+        const long long nblk = (k + kNb - 1) / kNb;
+        Dinv.ensure(8 * (size_t)nblk * kNb * kNb);
         // flip rows and columns: Mf[i][j] = M[k-1-i][k-1-j]; with M symmetric a flip of the flat array does it
         VecParams P = vp();
         P.op = VOP_FLIP; P.N = k * k; P.in = M; P.out = Mf.as<double>();
         vec_launch(ctx, rws, P);
         double* A = Mf.as<double>();
-        for (long long j0 = 0; j0 < k; j0 += kNb) {
-            const int nb = (int)std::min<long long>(kNb, k - j0);
-            tri(TRI_POTRF, A, k, nullptr, 0, (int)j0, nb, 0, 0, (int)k);
-            const int rest = (int)(k - j0 - nb);
+        for (long long J0 = 0; J0 < k; J0 += kOuter) {
+            const long long Jend = std::min<long long>(k, J0 + kOuter);
+            for (long long j0 = J0; j0 < Jend; j0 += kNb) {
+                const int nb = (int)std::min<long long>(kNb, k - j0);
+                double* di = Dinv.as<double>() + (j0 / kNb) * kNb * kNb;
+                tri(TRI_POTRF, A, k, nullptr, 0, (int)j0, nb, 0, 0, (int)k, di);
+                const long long c0 = j0 + nb;
+                const int rest = (int)(k - c0);
+                if (rest <= 0) continue;
+                // X_j = inv(R_jj)' A[j, c0:]  in place (one tile row: a block reads its own columns, then writes them)
+                double* Xj = A + j0 + c0 * k;
+                gemm(di, kNb, 1, Xj, 1, k, Xj, k, nb, rest, nb, 1.0, 0.0);
+                // rows of this panel below block j: A[c0:Jend, c0:] -= X_j[:, c0:Jend]' X_j   (upper block tiles)
+                const int mrows = (int)(Jend - c0);
+                if (mrows > 0) gemm(Xj, k, 1, Xj, 1, k, A + c0 + c0 * k, k, mrows, rest, nb, -1.0, 1.0, true);
+            }
+            // everything below the panel: A[Jend:, Jend:] -= X_J' X_J with X_J = A[J0:Jend, Jend:]
+            const int rest = (int)(k - Jend);
             if (rest > 0) {
-                tri(TRI_PANEL, A, k, A, k, (int)j0, nb, (int)(j0 + nb), rest, (int)k);
-                // trailing update A22 -= X'X, X = A[j0:j0+nb, j0+nb:]  (upper block tiles only)
-                const double* X = A + j0 + (j0 + nb) * k;
-                gemm(X, k, 1, X, 1, k, A + (j0 + nb) + (j0 + nb) * k, k, rest, rest, nb, -1.0, 1.0, true);
+                const double* XJ = A + J0 + Jend * k;
+                gemm(XJ, k, 1, XJ, 1, k, A + Jend + Jend * k, k, rest, rest, (int)(Jend - J0), -1.0, 1.0, true);
             }
         }
         have_chol = true;
     }
 
-    // X (k x ncols, leading dimension k) <- R^-1 X, blocked back substitution
+    // X (k x ncols, leading dimension k) <- R^-1 X, blocked back substitution with the same two levels:
+    // Y_j = inv(R_jj) X_j (GEMM, in place), rows of the outer panel above it updated with K = 64, everything above
+    // the panel with one K = 256 GEMM
     void back_solve(double* X, int ncols) {
         const double* A = Mf.as<double>();
-        const long long nblk = (k + kNb - 1) / kNb;
-        for (long long jb = nblk - 1; jb >= 0; --jb) {
-            const long long j0 = jb * kNb;
-            const int nb = (int)std::min<long long>(kNb, k - j0);
-            tri(TRI_BACK, Mf.as<double>(), k, X, k, (int)j0, nb, 0, ncols, (int)k);
-            // X[0:j0, :] -= R[0:j0, j0:j0+nb] Y_j
-            if (j0 > 0) gemm(A + j0 * k, 1, k, X + j0, 1, k, X, k, (int)j0, ncols, nb, -1.0, 1.0);
+        const long long npan = (k + kOuter - 1) / kOuter;
+        for (long long pb = npan - 1; pb >= 0; --pb) {
+            const long long J0 = pb * kOuter, Jend = std::min<long long>(k, J0 + kOuter);
+            const long long nin = (Jend - J0 + kNb - 1) / kNb;
+            for (long long ib = nin - 1; ib >= 0; --ib) {
+                const long long j0 = J0 + ib * kNb;
+                const int nb = (int)std::min<long long>(kNb, k - j0);
+                const double* di = Dinv.as<double>() + (j0 / kNb) * kNb * kNb;
+                // Y_j = inv(R_jj) X[j0:j0+nb, :]   (A-operand (i, l) = Dinv[i + l * 64])
+                gemm(di, 1, kNb, X + j0, 1, k, X + j0, k, nb, ncols, nb, 1.0, 0.0);
+                // X[J0:j0, :] -= R[J0:j0, j0:j0+nb] Y_j
+                if (j0 > J0) gemm(A + J0 + j0 * k, 1, k, X + j0, 1, k, X + J0, k, (int)(j0 - J0), ncols, nb, -1.0, 1.0);
+            }
+            // X[0:J0, :] -= R[0:J0, J0:Jend] Y_J
+            if (J0 > 0) gemm(A + J0 * k, 1, k, X + J0, 1, k, X, k, (int)J0, ncols, (int)(Jend - J0), -1.0, 1.0);
         }
     }
 

@@ -127,20 +127,30 @@ SIMT_DEVICE void gemm_body(const GemmParams& P, unsigned char* smem) {
         SIMT_SYNC();
     }
     // epilogue: lane holds C[row = lane/4][col = 2 (lane%4) + {0,1}] of each 8 x 8 tile
+    // The old values of C are fetched eight at a time BEFORE the stores of that group: element by element the
+    // compiler must keep every load behind the previous store (it cannot prove the addresses distinct), and 64
+    // dependent round trips cost more than the whole K loop of the rank-64 updates of the blocked Cholesky.
+    double* __restrict__ Cw = P.C;
+    const double* __restrict__ Cr = P.C;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 8; ++i) {
+        const int r = row0 + wm + 8 * i + (lane >> 2);
+        double old[4][2];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int r = row0 + wm + 8 * i + (lane >> 2);
                 const int c = col0 + wn + 8 * j + 2 * (lane & 3) + e;
-                if (r < P.M && c < P.N) {
-                    double* dst = P.C + (long long)c * P.ldc + r;
-                    const double old = (P.beta != 0.0) ? *dst : 0.0;
-                    *dst = P.alpha * acc[i][j][e] + P.beta * old;
-                }
+                old[j][e] = (P.beta != 0.0 && r < P.M && c < P.N) ? Cr[(long long)c * P.ldc + r] : 0.0;
             }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = col0 + wn + 8 * j + 2 * (lane & 3) + e;
+                if (r < P.M && c < P.N) Cw[(long long)c * P.ldc + r] = P.alpha * acc[i][j][e] + P.beta * old[j][e];
+            }
+    }
 }
 
 }  // namespace mgvi

@@ -38,7 +38,20 @@ def main():
         ctx.check(ctx.lib.sample_residuals_dense(model.handle, pkg.capi.ptr(Z), n, pkg.capi.ptr(R), None))
     _, prof_s, wall_s = profile(ctx, run)          # first call factorises
     _, prof_s2, wall_s2 = profile(ctx, run)        # factor cached: back substitution only
-    chol_ms = sum(v[0] for t, v in prof_s.items()) - sum(v[0] for t, v in prof_s2.items())
+    kernel_sum_ms = sum(v[0] for t, v in prof_s.items()) - sum(v[0] for t, v in prof_s2.items())
+    # what a caller waits for (no per-kernel events: their host overhead inflates ~200 short launches): wall clock of
+    # the synchronous call on a fresh model (factor + solve) minus the solve-only call, best of 3
+    t_first, t_solve = [], []
+    for _ in range(3):
+        m2 = pkg.model_from_config(cfg, ctx)
+        pkg.ResidualSampler(m2, cfg["center"], pkg.MatrixInversion(), ctx)
+        def run2():
+            ctx.check(ctx.lib.sample_residuals_dense(m2.handle, pkg.capi.ptr(Z), n, pkg.capi.ptr(R), None))
+        t0 = time.perf_counter(); run2(); t_first.append(time.perf_counter() - t0)
+        t0 = time.perf_counter(); run2(); t_solve.append(time.perf_counter() - t0)
+        m2.close()
+    chol_ms = (min(t_first) - min(t_solve)) * 1e3
+    solve_ms = min(t_solve) * 1e3
     trail_ms = prof_s.get(3001, (0, 0))[0]
     res, c_new = pkg.mgvi_step(model, cfg["data"], n, cfg["center"], pkg.MGVIConfig(linsolver=pkg.MatrixInversion()), ctx,
                                draws=cfg["Z"])
@@ -51,7 +64,8 @@ def main():
            "syrk_ms": syrk_ms, "syrk_tflops_symmetric_half": 0.5 * full / (syrk_ms * 1e-3) / 1e12 if syrk_ms else None,
            "syrk_tflops_full_product_equivalent": full / (syrk_ms * 1e-3) / 1e12 if syrk_ms else None,
            "cholesky_ms": chol_ms, "cholesky_tflops": (k ** 3 / 3.0) / (chol_ms * 1e-3) / 1e12 if chol_ms > 0 else None,
-           "cholesky_trailing_update_ms": trail_ms, "sample_ms_after_factor": sum(v[0] for v in prof_s2.values()),
+           "cholesky_kernel_time_sum_ms": kernel_sum_ms, "cholesky_trailing_update_ms": trail_ms,
+           "sample_ms_after_factor": solve_ms, "sample_kernel_time_sum_ms": sum(v[0] for v in prof_s2.values()),
            "model_create_wall_s": wall_c, "mgvi_step_s": step_s, "mnlp": res.mnlp,
            "kernels_create": prof_c, "kernels_first_sample": prof_s}
     print(json.dumps(out))
