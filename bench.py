@@ -617,8 +617,14 @@ def main():
              10: ("last_pass(H_last, c^2 A., +p, p.Ap)", ab["last"]),
              211: ("fused_1d(p update, A., H, w., H, A., +p, p.Ap)", ab["first"] + ab["last"] - 16 * N),
              1000: ("cg_update(x+=a p, r-=a Ap, r.r)", ab["update"]),
+             # deferred solution update: the update kernel streams r only (half of the update's
+             # share), x += a p rides in the next iteration's axis0_fused (credited there below), one flush at the end
+             1014: ("cg_update_r(r-=a Ap, r.r)", ab["update"] // 2),
+             1015: ("x_flush(x+=a p, pending samples)", 24 * N),
              400: ("rhs_first(q.n1, H)", 16 * N + 16 * N), 30: ("rhs_last(H, cA., +eta, b.b)", 16 * N + 40 * N),
              430: ("rhs_1d", 16 * N + 40 * N)}
+    if any(int(tags[i]) == 1014 for i in range(max(ntag, 0))):
+        names[1] = ("axis0_fused(H, w., H; x+=a p of the previous update)", ab["fused0"] + ab["update"] // 2)
     kern = []
     for i in range(max(ntag, 0)):
         tag, ms, cnt = int(tags[i]), float(tms[i]), int(tcnt[i])
@@ -640,7 +646,7 @@ def main():
                     "unit": "GB/s", "frac": dom["algorithmic_gbs"] / hbm_peak,
                     "traffic": None,
                     "traffic_note": "not measurable inside a timed run; the ncu --set full capture of this command is "
-                                    "profiles/r2_ncu_full_c3_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                                    "profiles/r2b_ncu_full_c3_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
                     "peak_source": peak_src, "share_of_step": dom["share"],
                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"]}
     # the whole Fisher-CG iteration against B_cg: what north_star's 60 % target is about
