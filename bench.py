@@ -635,6 +635,15 @@ def main():
             e["algorithmic_bytes_per_launch"] = per_sample * n_loc
             e["algorithmic_gbs"] = per_sample * n_loc / (avg_ms * 1e-3) / 1e9
         kern.append(e)
+    # bytes each CG kernel really moves per sample (ncu: nothing is re-read), next to the
+    # algorithmic share of SURVEY's pass model
+    moved_k = {200: 32 * N, 1: 16 * N, 0: 16 * N, 10: 24 * N, 1000: 48 * N, 1014: 24 * N}
+    if any(k["tag"] == 1014 for k in kern):
+        moved_k[1] = 40 * N
+    for k in kern:
+        if k["tag"] in moved_k and d >= 2:
+            k["moved_bytes_per_launch"] = moved_k[k["tag"]] * n_loc
+            k["moved_gbs"] = moved_k[k["tag"]] * n_loc / (k["avg_ms"] * 1e-3) / 1e9
     tot_ms = sum(k["avg_ms"] * k["launches"] for k in kern) or 1.0
     for k in kern:
         k["share"] = k["avg_ms"] * k["launches"] / tot_ms
@@ -649,6 +658,11 @@ def main():
                                     "profiles/r2b_ncu_full_c3_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
                     "peak_source": peak_src, "share_of_step": dom["share"],
                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"]}
+        if "moved_gbs" in dom:
+            # the same kernel against the bytes it really moves (the algorithmic model counts the fused axis-0
+            # transforms as two passes, so `frac` can exceed 1)
+            roofline["moved_bytes_per_launch"] = dom["moved_bytes_per_launch"]
+            roofline["frac_bytes_moved"] = dom["moved_gbs"] / hbm_peak
     # the whole Fisher-CG iteration against B_cg: what north_star's 60 % target is about
     per_iter_ms = dev_ms_max / (K * ITERS)
     cg_path = {"B_cg_bytes_per_sample_iteration": ab["B_cg"], "lockstep_iteration_ms": per_iter_ms,
