@@ -63,7 +63,10 @@ typedef struct {
     int32_t kind;
     /* ---- FIELD_DHT: s = scale * H(amplitude . xi) + offset, lambda = link(s) ---- */
     int32_t ndim;               /* 1..3 */
-    int64_t dims[3];            /* C order */
+    int64_t dims[3];            /* C order.  Any axis length up to 4096: power-of-two axes (>= 8) run the fused
+                                   fast passes, other lengths a Bluestein chirp-z pass on the same FFT core (axes of
+                                   <= 32 points a direct pass); a 1-D power-of-two line may be as long as 2^24
+                                   (four-step split).  Longer axes: MGVIB200_ERR_UNSUPPORTED. */
     const double* amplitude;    /* N */
     double scale;
     double offset;
