@@ -14,10 +14,10 @@ SIMT_GLOBAL(256) k_naive_axis(SIMT_KARGS(NaiveParams)) {
     naive_axis_body(P, simt_smem);
 }
 
-template <int MAXT>
-SIMT_GLOBAL2(MAXT, (MAXT <= 256 ? 2 : 1)) k_bluestein_axis(SIMT_KARGS(BlueParams)) {
+template <int MAXT, int LGM>
+SIMT_GLOBAL2(MAXT, (MAXT <= 256 ? 2 : 1)) k_bluestein_axis(SIMT_KARGS(BlueParams)) {      // 256: 128 registers, 512: 128, 1024: 64
     SIMT_SMEM_DECL
-    bluestein_axis_body(P, simt_smem);
+    bluestein_axis_body<LGM>(P, simt_smem);
 }
 
 namespace {
@@ -572,8 +572,16 @@ struct FieldEngine : Engine {
                 const size_t smem = kSmemHeader + ((size_t)16 << B.lg_m);
                 const long long grid = (B.nlines + 1) / 2;
                 ctx->prof_pre(6000 + a);
-                if (threads <= 256) rt_launch(k_bluestein_axis<256>, grid, threads, smem, ctx->stream, B);
-                else rt_launch(k_bluestein_axis<1024>, grid, threads, smem, ctx->stream, B);
+                // one build per padded length m = 2^lg_m (256 ... 8192)
+                switch (B.lg_m) {
+                    case 8: rt_launch(k_bluestein_axis<256, 8>, grid, threads, smem, ctx->stream, B); break;
+                    case 9: rt_launch(k_bluestein_axis<256, 9>, grid, threads, smem, ctx->stream, B); break;
+                    case 10: rt_launch(k_bluestein_axis<256, 10>, grid, threads, smem, ctx->stream, B); break;
+                    case 11: rt_launch(k_bluestein_axis<256, 11>, grid, threads, smem, ctx->stream, B); break;
+                    case 12: rt_launch(k_bluestein_axis<512, 12>, grid, threads, smem, ctx->stream, B); break;
+                    case 13: rt_launch(k_bluestein_axis<1024, 13>, grid, threads, smem, ctx->stream, B); break;
+                    default: throw RtError{"internal: Bluestein length out of range", 1};
+                }
                 ctx->prof_post();
                 ctx->launches++;
                 std::swap(cur, other);

@@ -913,9 +913,12 @@ struct BlueParams {
     int n, lg_m;
 };
 
+// LGM > 0 fixes log2(m) at compile time (stage loops unrolled, swizzle offsets folded into immediates).
+template <int LGM>
 SIMT_DEVICE void bluestein_axis_body(const BlueParams& P, unsigned char* smem_raw) {
     const int lt = SIMT_TID;
-    const int m8 = 1 << (P.lg_m - 3);
+    const int lg_m = LGM ? LGM : P.lg_m;
+    const int m8 = 1 << (lg_m - 3);
     LineView lv;
     lv.sm = reinterpret_cast<double2*>(smem_raw + kSmemHeader);
     lv.lgL = 0;
@@ -942,13 +945,13 @@ SIMT_DEVICE void bluestein_axis_body(const BlueParams& P, unsigned char* smem_ra
             v[t] = make_double2(0.0, 0.0);
         }
     }
-    fft_line_forward<0>(v, lv, lt, P.lg_m, P.tw);
+    fft_line_forward<LGM>(v, lv, lt, lg_m, P.tw);
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
         const double2 x = cmul(v[t], SIMT_LDG(P.hf + lt + t * m8));
         v[t] = make_double2(x.x, -x.y);
     }
-    fft_line_forward<0>(v, lv, lt, P.lg_m, P.tw);
+    fft_line_forward<LGM>(v, lv, lt, lg_m, P.tw);
     // shared memory now holds conj(convolution) in natural order; Z[k] = c_k * conj(.)
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
