@@ -452,13 +452,16 @@ SIMT_DEVICE void deferred_x_update(const FieldPassParams& P, int s, long long bt
     double2* __restrict__ x2 = reinterpret_cast<double2*>(P.xout) + o2;
     const double2* __restrict__ p2 = reinterpret_cast<const double2*>(P.x_prev_p) + o2;
     const int nt = SIMT_NTID;
-    for (long long i0 = tid; i0 < slab2; i0 += 4 * nt) {
-        double2 xv[4], pv[4];
+#ifndef MGVI_DEFER_UNROLL
+#define MGVI_DEFER_UNROLL 4
+#endif
+    for (long long i0 = tid; i0 < slab2; i0 += MGVI_DEFER_UNROLL * nt) {
+        double2 xv[MGVI_DEFER_UNROLL], pv[MGVI_DEFER_UNROLL];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < MGVI_DEFER_UNROLL; ++u)
             if (i0 + u * nt < slab2) { xv[u] = x2[i0 + u * nt]; pv[u] = p2[i0 + u * nt]; }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < MGVI_DEFER_UNROLL; ++u)
             if (i0 + u * nt < slab2) {
                 xv[u].x += alpha * pv[u].x; xv[u].y += alpha * pv[u].y;
                 x2[i0 + u * nt] = xv[u];
