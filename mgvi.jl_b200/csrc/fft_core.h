@@ -386,15 +386,34 @@ SIMT_DEVICE void fft_line_pre(double2 (&v)[8], const LineView& lv, int lt, const
     // leading radix-4 stage (Ns = 1): butterflies jA = lt and jB
     dft4(v[0], v[1], v[2], v[3]);
     dft4(v[4], v[5], v[6], v[7]);
+    if (lgL == 0) {
+        // one line per unit: this exchange gets a swizzle of its own, chunk ^= (chunk >> 3) & 3.  The descending
+        // jB runs (4 (n/4 - lt) + t) put two lanes of every quarter warp on the same bank group under the usual
+        // three-bit swizzle (ncu: 4 of the first pass's STS.128 at twice their ideal wavefronts); two bits folded
+        // into the slot bits keep jA writes, jB writes and the linear read-back conflict-free
+        // (tools/bank_conflicts_paired.py).  n/8 is a multiple of 32 chunks, so the read-back stays linear.
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        lv.at((lt << 2) + t) = v[t];
-        lv.at((jB << 2) + t) = v[4 + t];
+        for (int t = 0; t < 4; ++t) {
+            const int ca = (lt << 2) + t, cb = (jB << 2) + t;
+            lv.sm[ca ^ ((ca >> 3) & 3)] = v[t];
+            lv.sm[cb ^ ((cb >> 3) & 3)] = v[4 + t];
+        }
+        SIMT_SYNC();
+        const int r3 = lt ^ ((lt >> 3) & 3);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = lv.sm[r3 + m * n8];
+        SIMT_SYNC();
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            lv.at((lt << 2) + t) = v[t];
+            lv.at((jB << 2) + t) = v[4 + t];
+        }
+        SIMT_SYNC();
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = lv.sm[rd_fast ? rd0 + m * rd_step : lv.idx(lt + m * n8)];
+        SIMT_SYNC();
     }
-    SIMT_SYNC();
-#pragma unroll
-    for (int m = 0; m < 8; ++m) v[m] = lv.sm[rd_fast ? rd0 + m * rd_step : lv.idx(lt + m * n8)];
-    SIMT_SYNC();
 #pragma unroll
     for (int lgNs = 2; lgNs < LG; lgNs += 3) {
         const int jlo = lt & ((1 << lgNs) - 1);
