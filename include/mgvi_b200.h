@@ -65,8 +65,9 @@ typedef struct {
     int32_t ndim;               /* 1..3 */
     int64_t dims[3];            /* C order.  Any axis length up to 4096: power-of-two axes (>= 8) run the fused
                                    fast passes, other lengths a Bluestein chirp-z pass on the same FFT core (axes of
-                                   <= 32 points a direct pass); a 1-D power-of-two line may be as long as 2^24
-                                   (four-step split).  Longer axes: MGVIB200_ERR_UNSUPPORTED. */
+                                   <= 32 points a direct pass); power-of-two axes of 2-D / 3-D fields may be as long
+                                   as 8192, a 1-D power-of-two line as long as 2^24 (four-step split).  Longer axes:
+                                   MGVIB200_ERR_UNSUPPORTED. */
     const double* amplitude;    /* N */
     double scale;
     double offset;

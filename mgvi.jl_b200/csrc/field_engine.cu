@@ -27,7 +27,8 @@ namespace {
 #endif
 const int kNaiveMaxAxis = 4096;
 long long kBlueMinAxis = 32;           // (MGVIB200_BLUE_MIN overrides: measurements against the direct pass) generic path: axes longer than this take the O(m log m) Bluestein pass, shorter ones the direct O(n^2) one
-const long long kFastMaxAxis = 4096;
+const long long kFastMaxAxis = 4096;        // 1-D: longest line one block transforms (longer power-of-two lines: four-step split)
+const long long kFastMaxAxisND = 8192;      // 2-D / 3-D: longest power-of-two axis (one complex line = 128 KB of shared memory, 1024 threads)
 const long long kDenseFieldMax = 8192;
 
 bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -243,7 +244,7 @@ struct FieldEngine : Engine {
         z1_stride = (layout == MGVIB200_LAYOUT_INTERLEAVED) ? 2 : 1;
         fast = true;
         for (int i = 0; i < ndim; ++i)
-            if (!is_pow2(dims[i]) || dims[i] < 8 || dims[i] > kFastMaxAxis) fast = false;
+            if (!is_pow2(dims[i]) || dims[i] < 8 || dims[i] > (ndim >= 2 ? kFastMaxAxisND : kFastMaxAxis)) fast = false;
         long long big_min = kFastMaxAxis + 1;     // tests lower this to run the four-step path at small sizes
         if (const char* e = getenv("MGVIB200_BIG_MIN")) big_min = std::max<long long>(64, atoll(e));
         if (ndim == 1 && is_pow2(N) && N >= big_min && N <= kFastMaxAxis * kFastMaxAxis) {
@@ -271,7 +272,7 @@ struct FieldEngine : Engine {
         if (!fast)
             for (int i = 0; i < ndim; ++i)
                 if (dims[i] > kNaiveMaxAxis)
-                    throw RtError{"FIELD_DHT: axis length must be a power of two in [8, 4096] or <= 4096", 3};
+                    throw RtError{"FIELD_DHT: axis length must be <= 4096, or a power of two <= 8192 (2-D / 3-D) / <= 2^24 (1-D)", 3};
         A.ensure(sizeof(double) * N);
         data.ensure(sizeof(double) * N);
         rt_h2d(A.p, d.amplitude, sizeof(double) * N, ctx->stream);

@@ -349,6 +349,22 @@ def test_deferred_solution_update_is_bitwise_the_plain_one(pkg, emu_ctx, monkeyp
         assert np.linalg.norm(out["1"][0][0][:, i] - Ro[:, i]) <= 1e-8 * np.linalg.norm(Ro[:, i]) + 2e-9
 
 
+@pytest.mark.parametrize("dims", [(8192, 8), (8, 8192)])
+def test_longest_power_of_two_axes(pkg, emu_ctx, dims):
+    """8192-point axes (2-D / 3-D limit): 1024 threads per line, 128 KB of shared memory per block."""
+    cfg = _field(pkg, dims, "LIKE_POISSON", 1)
+    m = pkg.model_from_config(cfg, emu_ctx)
+    om = oracle_model(cfg)
+    s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(abstol=0.0, reltol=0.0, maxiters=3), emu_ctx)
+    V = np.random.default_rng(1).standard_normal((m.n_theta, 1))
+    lin = om.linearize(cfg["center"])
+    assert rel(s.metric_apply(V)[:, 0], O.metric_apply(lin, V[:, 0])) < 1e-12
+    R = pkg.sample_residuals(s, 1, draws=(cfg["Z1"], cfg["Z2"]))
+    Ro, _, _ = O.sample_residuals_cg(om, cfg["center"], cfg["Z1"], cfg["Z2"], atol=0.0, rtol=0.0, itmax=3)
+    assert rel(R, Ro) < RTOL
+    m.close()
+
+
 def test_bluestein_converged_partner_is_masked(pkg, emu_ctx):
     """Two residual samples of a 1-D any-length field share one complex transform.  Once one of them has
     converged its line must leave the transform (a stale line is transformed over and over, grows by ~1e6 per

@@ -191,10 +191,13 @@ def test_full_size_c3_2048x2048(pkg, gpu_ctx):
 
 
 @pytest.mark.parametrize("dims,like", [((4096, 4096), "LIKE_POISSON"), ((2048, 512), "LIKE_NORMAL"),
-                                       ((512, 2048), "LIKE_POISSON"), ((1024, 4096), "LIKE_NORMAL")])
+                                       ((512, 2048), "LIKE_POISSON"), ((1024, 4096), "LIKE_NORMAL"),
+                                       ((8192, 512), "LIKE_POISSON"), ((256, 8192), "LIKE_NORMAL"),
+                                       ((16, 8192, 16), "LIKE_POISSON")])
 def test_large_2d_shapes(pkg, gpu_ctx, dims, like):
-    """Largest supported axis lengths and non-square fields: 1024-thread column tiles, tile-major
-    scratch with 2- and 4-column tiles next to natural-layout 8-column tiles."""
+    """Largest supported axis lengths (8192 points in 2-D / 3-D: one complex line fills 128 KB of shared memory)
+    and non-square fields: 1024-thread column tiles, tile-major scratch with 2- and 4-column tiles next to
+    natural-layout 8-column tiles."""
     cfg = _field(pkg, dims, like, 1)
     _full_metric_checks(pkg, gpu_ctx, cfg, 1)
 
