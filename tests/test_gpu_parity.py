@@ -130,7 +130,7 @@ def test_many_residuals_lockstep_masking(pkg, gpu_ctx):
     m.close()
 
 
-@pytest.mark.parametrize("dims", [(2048, 32), (1024, 256), (64, 32, 16)])
+@pytest.mark.parametrize("dims", [(2048, 32), (1024, 256), (64, 32, 16), (2048, 2048)])
 def test_deferred_solution_update_bitwise(pkg, gpu_ctx, monkeypatch, dims):
     """x += alpha p inside the fused axis-0 pass of the next iteration (field_pass.h: defer_x; default for 2-D
     fields with a long axis 0, forced here for the others) against the streaming update kernel: bit for bit,
