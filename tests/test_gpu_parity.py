@@ -347,7 +347,19 @@ def _random_shapes(seed, count):
     return out
 
 
-@pytest.mark.parametrize("dims", _random_shapes(7, 16))
+def _random_shapes_any_length(seed, count):
+    """like _random_shapes, with axis lengths on both sides of the Bluestein threshold (32) and of powers of two"""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < count:
+        d = int(rng.integers(1, 4))
+        dims = tuple(int(rng.choice([2, 7, 16, 31, 33, 40, 63, 64, 65, 100, 127, 129, 250, 256, 1000])) for _ in range(d))
+        if 2 <= int(np.prod(dims)) <= 70000:
+            out.append(dims)
+    return out
+
+
+@pytest.mark.parametrize("dims", _random_shapes(7, 16) + _random_shapes_any_length(11, 14))
 def test_random_shapes(pkg, gpu_ctx, dims):
     """Seeded random shapes (power-of-two and other axis lengths, 1-D to 3-D): metric product and
     CG residual samples against the oracle."""
@@ -361,9 +373,13 @@ def test_random_shapes(pkg, gpu_ctx, dims):
     lin = om.linearize(cfg["center"])
     MVo = np.stack([O.metric_apply(lin, V[:, i]) for i in range(2)], axis=1)
     assert rel(s.metric_apply(V), MVo) < 1e-12, dims
-    R = pkg.sample_residuals(s, 3, draws=(cfg["Z1"], cfg["Z2"]))
-    Ro, _, _ = O.sample_residuals_cg(om, cfg["center"], cfg["Z1"], cfg["Z2"], **TIGHT_O)
-    assert rel(R, Ro) < RTOL, dims
+    R, info = pkg.sample_residuals(s, 3, draws=(cfg["Z1"], cfg["Z2"]), return_info=True)
+    Ro, ito, _ = O.sample_residuals_cg(om, cfg["center"], cfg["Z1"], cfg["Z2"], **TIGHT_O)
+    # tiny fields: the solve runs into the reference's iteration cap (itmax = n_theta) before reltol 1e-12; the last
+    # iterates of such a truncated CG amplify rounding (measured on the emulator at 16 pixels: 3e-11 between two
+    # correct implementations), so only there the bar is 1e-8
+    capped = bool(np.any(ito >= om.n_theta))
+    assert rel(R, Ro) < (1e-8 if capped else RTOL), (dims, info["iters"], ito)
     m.close()
 
 
