@@ -104,6 +104,28 @@ struct FieldEngine : Engine {
     CgGraphKey cg_graph_key{};
     int64_t cg_graph_launches = 0;
     bool graphs_on = true;          // MGVIB200_GRAPH=0 launches every kernel from the host
+    // Two concurrent sample groups (sample_cg_grouped): with few samples per GPU (the 8-GPU share of C3 is 4) a
+    // lock-step kernel is only ~9 waves of blocks and its ramp-up / tail is a visible fraction; two independent
+    // half-size solves on two streams fill each other's tails (measured: 8 775 -> 9 149 sample-iterations/s at 4 samples)
+    struct CgGroup {
+        int off = 0, n = 0;
+        rt_stream st{};
+        ReduceWs rws;
+        DevBuf tile;
+        rt_graph graph{};
+        bool gvalid = false;
+        CgGraphKey key{};
+        int64_t glaunch = 0;
+        rt_event ev[2]{}, ev_done{};
+        int slot = 0;
+        bool pending = false, done = false;
+        long long it = 0;
+        CgScalars sc{};
+        int* h = nullptr;
+    };
+    CgGroup grp[2];
+    bool groups_ready = false;
+    int groups_mode = -1;             // MGVIB200_GROUPS: -1 auto (few waves per kernel), 1 never, 2 always (2-D / 3-D fast path)
     int big_block_threads = 64;     // (measured at C2: 64 -> 0.0475 ms per iteration, 256 -> 0.0490) MGVIB200_BIG_THREADS: target block size of the four-step kernels (units per block = this / unit size)
     int big_ap_lgL = 3;             // MGVIB200_BIG_AP_LGL: log2(lines per unit) of the column kernel A' (1 = one column pair)
     // MGVIB200_PERSIST=1: one persistent cooperative kernel per solve for L2-resident long 1-D fields.  Measured on
@@ -118,6 +140,11 @@ struct FieldEngine : Engine {
 
     ~FieldEngine() override {
         if (cg_graph_valid) rt_graph_destroy(cg_graph);
+        for (auto& G : grp) {
+            if (G.gvalid) rt_graph_destroy(G.graph);
+            G.rws.release(); G.tile.release();
+            if (groups_ready) { rt_stream_destroy(G.st); rt_event_destroy(G.ev[0]); rt_event_destroy(G.ev[1]); rt_event_destroy(G.ev_done); }
+        }
         dense_chol_destroy(chol);
         Mdense.release(); eye.release();
         DevBuf* all[] = {&A, &data, &w, &q, &wbar, &center, &w_tiled, &ws_tile, &ws_r, &ws_p, &ws_p2, &ws_t, &pt_t, &gather, &sc_gather, &kl_red, &qsum, &n_x, &n_r,
@@ -263,6 +290,7 @@ struct FieldEngine : Engine {
         if (const char* e = getenv("MGVIB200_GRAPH")) graphs_on = atoi(e) != 0;
         if (const char* e = getenv("MGVIB200_PF")) use_paired = atoi(e) != 0;
         if (const char* e = getenv("MGVIB200_PERSIST")) persist_on = atoi(e) != 0;
+        if (const char* e = getenv("MGVIB200_GROUPS")) groups_mode = atoi(e);
         if (const char* e = getenv("MGVIB200_DEFER_X")) { defer_on = atoi(e) != 0; defer_force = defer_on; if (atoi(e) > 0) defer_mode = std::min(2, atoi(e)); }
         if (const char* e = getenv("MGVIB200_BLUE_MIN")) kBlueMinAxis = std::max<long long>(1, atoll(e));
         if (const char* e = getenv("MGVIB200_BIG_THREADS")) big_block_threads = std::max(32, atoi(e));
@@ -721,6 +749,27 @@ struct FieldEngine : Engine {
         }
     }
 
+    // Tile-major layout of the 2-D metric product (field_pass.h): decides whether it applies and keeps the re-laid
+    // copy of the weight `wsrc` current (one VOP_TILE launch per linearisation, on the current stream).
+    bool tiled_weight(const double* wsrc, int nvec, int& lg_wt, int& lg_rows) {
+        lg_wt = 0; lg_rows = 0;
+        if (!(ndim == 2 && tiled_mode != 0)) return false;
+        const PassGeo g0 = geo_axis(0, nvec);
+        const long long wt = 2LL * g0.L;
+        if (!(g0.geo == GEO_STRIDED && (tiled_mode == 1 || wt < 16) && (dims[1] / 8) % wt == 0 && dims[1] >= 8 * wt)) return false;
+        lg_wt = ilog2((int)wt); lg_rows = g0.log2n;
+        if (w_tiled_src != wsrc || w_tiled_gen != w_gen || w_tiled_lg_wt != lg_wt) {
+            w_tiled.ensure(sizeof(double) * N);
+            VecParams T;
+            memset(&T, 0, sizeof T);
+            T.op = VOP_TILE; T.nvec = 1; T.N = N; T.in = wsrc; T.out = w_tiled.as<double>();
+            T.lg_wt = lg_wt; T.lg_rows = lg_rows; T.lg_cols = ilog2((int)dims[1]);
+            vec_launch(ctx, rws, T);
+            w_tiled_src = wsrc; w_tiled_gen = w_gen; w_tiled_lg_wt = lg_wt;
+        }
+        return true;
+    }
+
     // M v = v + c^2 A . H( w . H(A . v) ), 2d-1 passes.  P carries PRO operands, vin, out, w.
     template <int PRO>
     void chain_metric(FieldPassParams P, int nvec, double* scratch, int fin, double* red) {
@@ -747,27 +796,13 @@ struct FieldEngine : Engine {
         // 2-D with narrow column tiles (rows of 2L reals < one 128-byte line): keep the scratch and the
         // weight tile-major so the column pass reads and writes whole lines (field_pass.h)
         int lg_wt = 0, lg_rows = 0;
-        if (ndim == 2 && tiled_mode != 0) {
-            const PassGeo g0 = geo_axis(0, nvec);
-            const long long wt = 2LL * g0.L;
-            if (g0.geo == GEO_STRIDED && (tiled_mode == 1 || wt < 16) && (dims[1] / 8) % wt == 0 && dims[1] >= 8 * wt) {
-                lg_wt = ilog2((int)wt); lg_rows = g0.log2n;
-                if (w_tiled_src != P.w || w_tiled_gen != w_gen || w_tiled_lg_wt != lg_wt) {
-                    w_tiled.ensure(sizeof(double) * N);
-                    VecParams T;
-                    memset(&T, 0, sizeof T);
-                    T.op = VOP_TILE; T.nvec = 1; T.N = N; T.in = P.w; T.out = w_tiled.as<double>();
-                    T.lg_wt = lg_wt; T.lg_rows = lg_rows; T.lg_cols = ilog2((int)dims[1]);
-                    vec_launch(ctx, rws, T);
-                    w_tiled_src = P.w; w_tiled_gen = w_gen; w_tiled_lg_wt = lg_wt;
-                }
-                // the CG chains write A p over their scratch (same rows in, same rows out); with the
-                // scratch tile-major the last pass would overwrite tiles other blocks still have to
-                // read, so the scratch becomes a buffer of its own
-                if (scratch == P.out) {
-                    ws_tile.ensure(sizeof(double) * N * nvec);
-                    scratch = ws_tile.as<double>();
-                }
+        if (tiled_weight(P.w, nvec, lg_wt, lg_rows)) {
+            // the CG chains write A p over their scratch (same rows in, same rows out); with the
+            // scratch tile-major the last pass would overwrite tiles other blocks still have to
+            // read, so the scratch becomes a buffer of its own
+            if (scratch == P.out) {
+                ws_tile.ensure(sizeof(double) * N * nvec);
+                scratch = ws_tile.as<double>();
             }
         }
         {
@@ -844,6 +879,7 @@ struct FieldEngine : Engine {
                    int64_t* iters_host, double* rnorm_host) override {
         check_pairing(n);
         const int nvec = (int)n;
+        if (use_groups(nvec)) { sample_cg_grouped(Z1, Z2, nvec, o, R, iters_host, rnorm_host); return; }
         const size_t vb = sizeof(double) * N * nvec;
         ws_r.ensure(vb); ws_p.ensure(vb); ws_t.ensure(vb);
         cgws.ensure(nvec);
@@ -966,6 +1002,175 @@ struct FieldEngine : Engine {
         // deferred mode: vectors that stopped in the very last launched update still lack its alpha p
         // (`it` iterations were launched; the last one built p in buffer (it - 1) % 2)
         if (defer && it > 0) vec_x_flush(ctx, rws, sc, R, pbuf[(it - 1) & 1], N, nvec);
+        rt_event_record(ctx->ev1, ctx->stream);
+        std::vector<int> hi(nvec);
+        std::vector<double> hr(nvec);
+        rt_d2h(hi.data(), cgws.iters.p, sizeof(int) * nvec, ctx->stream);
+        rt_d2h(hr.data(), cgws.rnorm.p, sizeof(double) * nvec, ctx->stream);
+        rt_sync(ctx->stream);
+        ctx->sampler_ms = rt_event_ms(ctx->ev0, ctx->ev1);
+        long long mx = 0;
+        for (int i = 0; i < nvec; ++i) {
+            if (iters_host) iters_host[i] = hi[i];
+            if (rnorm_host) rnorm_host[i] = hr[i];
+            mx = std::max<long long>(mx, hi[i]);
+        }
+        ctx->lockstep_iters = mx;
+    }
+
+    bool use_groups(int nvec) const {
+        if (!rt_has_graphs || !graphs_on || ctx->profile || !fast || big || ndim < 2 || nvec < 2 || groups_mode == 1) return false;
+        if (groups_mode == 2) return true;
+        // auto: the row pass of the whole batch is fewer than ~100 waves of resident blocks (measured at C3: 4 samples
+        // 0.442 -> 0.416 ms per iteration, 8 samples 0.838 -> 0.809, 32 samples 3.382 -> 3.355; profiles/README.md)
+        const PassGeo g = geo_axis(ndim - 1, nvec);
+        return (double)g.ntb * nvec < 100.0 * MGVI_MINB * ctx->sm_count;
+    }
+
+    // The sampler's batched CG as two independent lock-step solves (samples [0, nA) and [nA, nvec)) on two streams,
+    // issued alternately by this thread: same kernels, same per-sample arithmetic and reduction order (results are
+    // bit-for-bit those of the single-stream path), the blocks of one group fill the ramp-up and tail of the other's
+    // kernels.  Each group has its own stream, reduction workspace, tile scratch, active counter and CUDA graph.
+    void sample_cg_grouped(const double* Z1, const double* Z2, int nvec, const mgvib200_cg_opts& o, double* R,
+                           int64_t* iters_host, double* rnorm_host) {
+        const size_t vb = sizeof(double) * N * nvec;
+        ws_r.ensure(vb); ws_p.ensure(vb); ws_t.ensure(vb);
+        cgws.ensure(nvec);
+        const long long itmax = o.maxiters > 0 ? o.maxiters : N;
+        const bool defer = (defer_force || (defer_on && ndim == 2 && dims[0] >= 1024)) && (N & 1) == 0;
+        cgws.defer = defer;
+        if (defer) {
+            ws_p2.ensure(vb);
+            rt_memset(cgws.x_pending.p, 0, sizeof(int) * nvec, ctx->stream);
+            rt_memset(cgws.x_count.p, 0, sizeof(int) * nvec, ctx->stream);
+        }
+        rt_memset(cgws.n_active.p, 0, sizeof(int) * 4, ctx->stream);
+        if (!groups_ready) {
+            for (auto& G : grp) { G.st = rt_stream_create(); G.ev[0] = rt_event_create(); G.ev[1] = rt_event_create(); G.ev_done = rt_event_create(); }
+            groups_ready = true;
+        }
+        { int a, b; tiled_weight(w.as<double>(), nvec, a, b); }      // the shared re-laid weight, before the streams fork
+        rt_event_record(ctx->ev0, ctx->stream);
+        const CgScalars sc_all = cgws.scalars(o.abstol, o.reltol, itmax, CG_KRYLOV);
+        const int nA = (nvec + 1) / 2;
+        for (int g = 0; g < 2; ++g) {
+            CgGroup& G = grp[g];
+            G.off = g ? nA : 0; G.n = g ? nvec - nA : nA;
+            G.sc = sc_all;
+            G.sc.gamma += G.off; G.sc.alpha += G.off; G.sc.beta += G.off; G.sc.eps += G.off; G.sc.rnorm += G.off;
+            G.sc.pAp += G.off; G.sc.iters += G.off; G.sc.active += G.off; G.sc.n_active += g;
+            if (defer) { G.sc.x_pending += G.off; G.sc.x_count += G.off; }
+            G.h = ctx->h_pinned + 64 * (1 + g);
+            G.slot = 0; G.pending = false; G.done = false; G.it = 0;
+            rt_stream_wait(G.st, ctx->ev0);
+        }
+        rt_stream main = ctx->stream;
+        auto enter = [&](CgGroup& G) { ctx->stream = G.st; std::swap(rws, G.rws); std::swap(ws_tile, G.tile); };
+        auto leave = [&](CgGroup& G) { std::swap(rws, G.rws); std::swap(ws_tile, G.tile); ctx->stream = main; };
+        auto vecs = [&](CgGroup& G, DevBuf& b) { return b.as<double>() + (size_t)G.off * N; };
+        auto launch_iter = [&](CgGroup& G, bool first, long long k) {
+            FieldPassParams P = base_params();
+            double* pb[2] = {vecs(G, ws_p), defer ? vecs(G, ws_p2) : vecs(G, ws_p)};
+            double* p_cur = pb[k & 1];
+            double* p_prev = pb[(k & 1) ^ 1];
+            double* Rg = R + (size_t)G.off * N;
+            P.r = vecs(G, ws_r);
+            P.p = first ? p_cur : p_prev;
+            P.p_out = defer ? p_cur : nullptr;
+            P.vin = p_cur; P.vin_ld = N;
+            P.out = vecs(G, ws_t); P.out_ld = N;
+            P.w = w.as<double>();
+            P.first_iter = first ? 1 : 0;
+            P.cg = G.sc;
+            P.mask_active = 1;
+            if (defer) { P.defer_x = defer_mode; P.x_prev_p = p_prev; P.xout = Rg; }
+            chain_metric<PRO_CG>(P, G.n, vecs(G, ws_t), FIN_CG_PAP, nullptr);
+            if (defer) vec_cg_update_r(ctx, rws, G.sc, vecs(G, ws_r), vecs(G, ws_t), N, G.n);
+            else vec_cg_update(ctx, rws, G.sc, Rg, vecs(G, ws_r), vecs(G, ws_p), vecs(G, ws_t), N, G.n);
+        };
+        // right-hand sides, first iteration and (once per shape) graph capture, group after group
+        for (int g = 0; g < 2; ++g) {
+            CgGroup& G = grp[g];
+            enter(G);
+            try {
+                FieldPassParams P = base_params();
+                P.q = q.as<double>(); P.Z1 = Z1 + (size_t)G.off * z1_ld; P.Z1_ld = z1_ld; P.Z1_off = 0; P.Z1_stride = z1_stride;
+                P.Z2 = Z2 + (size_t)G.off * N; P.Z2_ld = N;
+                P.r = vecs(G, ws_r); P.p = vecs(G, ws_p); P.xout = R + (size_t)G.off * N;
+                P.scale = c * pow(0.5, ndim);
+                P.cg = G.sc;
+                chain_adjoint<PRO_RHS, EPI_RHS>(P, G.n, vecs(G, ws_t), FIN_RHS, nullptr);
+                G.h[0] = 1;
+                rt_d2h(G.h, G.sc.n_active, sizeof(int), ctx->stream);
+            } catch (...) { leave(G); throw; }
+            leave(G);
+        }
+        for (int g = 0; g < 2; ++g) {
+            CgGroup& G = grp[g];
+            rt_sync(G.st);
+            if (!(G.h[0] > 0 && itmax > 0)) { G.done = true; continue; }
+            enter(G);
+            try {
+                launch_iter(G, true, 0);
+                G.it = 1;
+                if (G.it >= itmax) { G.done = true; }
+                else {
+                    const CgGraphKey key{R + (size_t)G.off * N, vecs(G, ws_r), vecs(G, ws_p), defer ? (void*)vecs(G, ws_p2) : nullptr,
+                                         vecs(G, ws_t), ws_tile.p, w_tiled.p, tmpA.p, tmpB.p, cs.p, rws.partials.p,
+                                         rws.counters.p, G.n, o.abstol, o.reltol, itmax};
+                    if (!G.gvalid || !(key == G.key)) {
+                        if (G.gvalid) { rt_graph_destroy(G.graph); G.gvalid = false; }
+                        const int64_t l0 = ctx->launches;
+                        rt_capture_begin(ctx->stream);
+                        try {
+                            for (int k = 0; k < kCgChunk; ++k) launch_iter(G, false, 1 + k);
+                            G.graph = rt_capture_end(ctx->stream);
+                        } catch (...) {
+                            rt_capture_abort(ctx->stream);
+                            throw;
+                        }
+                        G.glaunch = ctx->launches - l0;
+                        ctx->launches = l0;
+                        G.key = key;
+                        G.gvalid = true;
+                    }
+                }
+            } catch (...) { leave(G); throw; }
+            leave(G);
+        }
+        // replay: one chunk per group in turn, each group polled one chunk behind its launches
+        const long long it_cap = itmax + 2 * kCgChunk;
+        while (!(grp[0].done && grp[1].done)) {
+            for (int g = 0; g < 2; ++g) {
+                CgGroup& G = grp[g];
+                if (G.done) continue;
+                rt_graph_launch(G.graph, G.st);
+                ctx->launches += G.glaunch;
+                G.it += kCgChunk;
+                rt_d2h(G.h + 16 * (1 + G.slot), G.sc.n_active, sizeof(int), G.st);
+                rt_event_record(G.ev[G.slot], G.st);
+                if (G.pending) {
+                    rt_event_sync(G.ev[G.slot ^ 1]);
+                    if (G.h[16 * (1 + (G.slot ^ 1))] <= 0) { G.done = true; continue; }
+                }
+                if (G.it >= it_cap) { G.done = true; continue; }
+                G.pending = true;
+                G.slot ^= 1;
+            }
+        }
+        for (int g = 0; g < 2; ++g) {
+            CgGroup& G = grp[g];
+            enter(G);
+            try {
+                if (defer && G.it > 0) {
+                    double* pb[2] = {vecs(G, ws_p), vecs(G, ws_p2)};
+                    vec_x_flush(ctx, rws, G.sc, R + (size_t)G.off * N, pb[(G.it - 1) & 1], N, G.n);
+                }
+                rt_event_record(G.ev_done, ctx->stream);
+            } catch (...) { leave(G); throw; }
+            leave(G);
+            rt_stream_wait(ctx->stream, G.ev_done);
+        }
         rt_event_record(ctx->ev1, ctx->stream);
         std::vector<int> hi(nvec);
         std::vector<double> hr(nvec);

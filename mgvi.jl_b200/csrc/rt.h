@@ -140,6 +140,8 @@ inline void rt_capture_abort(rt_stream s) { cudaGraph_t g = nullptr; cudaStreamE
 inline void rt_graph_launch(rt_graph g, rt_stream s) { RT_CUDA(cudaGraphLaunch(g, s)); }
 inline void rt_graph_destroy(rt_graph g) { if (g) cudaGraphExecDestroy(g); }
 inline void rt_event_sync(rt_event e) { RT_CUDA(cudaEventSynchronize(e)); }
+// make `s` wait (on the device) for everything recorded into `e`
+inline void rt_stream_wait(rt_stream s, rt_event e) { RT_CUDA(cudaStreamWaitEvent(s, e, 0)); }
 
 #else  // ---------------------------------- emulation --------------------------------------------
 
@@ -202,6 +204,7 @@ inline void rt_capture_abort(rt_stream) {}
 inline void rt_graph_launch(rt_graph, rt_stream) {}
 inline void rt_graph_destroy(rt_graph) {}
 inline void rt_event_sync(rt_event) {}
+inline void rt_stream_wait(rt_stream, rt_event) {}      // the emulator executes launches in program order
 
 template <typename K, typename P>
 inline void rt_launch(K kernel, long long grid, int block, size_t smem, rt_stream, const P& params);

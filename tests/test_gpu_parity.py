@@ -157,6 +157,34 @@ def test_deferred_solution_update_bitwise(pkg, gpu_ctx, monkeypatch, dims):
     assert len(set(out["1"][0][1].tolist())) >= 3
 
 
+@pytest.mark.parametrize("dims,n", [((2048, 64), 4), ((256, 256), 5), ((32, 64, 16), 3), ((1024, 1024), 2), ((64, 64), 7)])
+def test_two_sample_groups_bitwise(pkg, gpu_ctx, monkeypatch, dims, n):
+    """Few samples per GPU: the batched CG runs as two independent lock-step solves on two streams
+    (field_engine.cu: sample_cg_grouped).  Same kernels, same per-sample arithmetic: residuals, iteration counts
+    and final residual norms must equal the single-stream path bit for bit -- odd sample counts, samples that
+    converge at different iterations, iteration caps inside and at the end of a replayed chunk."""
+    cfg = _field(pkg, dims, "LIKE_POISSON", n)
+    scale = np.logspace(-5, 2, n)
+    Z1, Z2 = cfg["Z1"] * scale, cfg["Z2"] * scale
+    out = {}
+    for mode in ("1", "2"):
+        monkeypatch.setenv("MGVIB200_GROUPS", mode)
+        m = pkg.model_from_config(cfg, gpu_ctx)
+        res = []
+        for opts in (dict(abstol=1e-9, reltol=1e-12), dict(abstol=0.0, reltol=0.0, maxiters=1),
+                     dict(abstol=0.0, reltol=0.0, maxiters=9), dict(abstol=0.0, reltol=0.0, maxiters=17),
+                     dict(abstol=1e-3, reltol=0.0, maxiters=40)):
+            s = pkg.ResidualSampler(m, cfg["center"], pkg.B200CG(**opts), gpu_ctx)
+            R, info = pkg.sample_residuals(s, n, draws=(Z1, Z2), return_info=True)
+            res.append((R.copy(), info["iters"].copy(), info["final_rnorm"].copy()))
+        out[mode] = res
+        m.close()
+    for (Ra, ia, ra), (Rb, ib, rb) in zip(out["1"], out["2"]):
+        assert np.array_equal(ia, ib) and np.array_equal(Ra, Rb)
+        if ra is not None:
+            assert np.array_equal(ra, rb)
+
+
 # ---- BASELINE.json full sizes -------------------------------------------------------------------
 def _full_metric_checks(pkg, gpu_ctx, cfg, n_solve):
     m = pkg.model_from_config(cfg, gpu_ctx)
