@@ -111,7 +111,7 @@ struct FieldEngine : Engine {
         int off = 0, n = 0;
         rt_stream st{};
         ReduceWs rws;
-        DevBuf tile;
+        DevBuf tile, cs;                  // tile-major scratch (2-D) / complex scratch of the four-step path (long 1-D)
         rt_graph graph{};
         bool gvalid = false;
         CgGraphKey key{};
@@ -142,7 +142,7 @@ struct FieldEngine : Engine {
         if (cg_graph_valid) rt_graph_destroy(cg_graph);
         for (auto& G : grp) {
             if (G.gvalid) rt_graph_destroy(G.graph);
-            G.rws.release(); G.tile.release();
+            G.rws.release(); G.tile.release(); G.cs.release();
             if (groups_ready) { rt_stream_destroy(G.st); rt_event_destroy(G.ev[0]); rt_event_destroy(G.ev[1]); rt_event_destroy(G.ev_done); }
         }
         dense_chol_destroy(chol);
@@ -1019,7 +1019,13 @@ struct FieldEngine : Engine {
     }
 
     bool use_groups(int nvec) const {
-        if (!rt_has_graphs || !graphs_on || ctx->profile || !fast || big || ndim < 2 || nvec < 2 || groups_mode == 1) return false;
+        if (!rt_has_graphs || !graphs_on || ctx->profile || !fast || nvec < 2 || groups_mode == 1) return false;
+        if (ndim == 1) {
+            // 1-D fields pair two samples per complex transform: split at a pair boundary (same partners, same bits),
+            // at least one pair per group.  Measured at C2 (16 samples): 0.0481 ms per iteration in one group, 0.0487 ms
+            // in two -- no gain, so only on request
+            return nvec >= 4 && groups_mode == 2;
+        }
         if (groups_mode == 2) return true;
         // auto: the row pass of the whole batch is fewer than ~100 waves of resident blocks (measured at C3: 4 samples
         // 0.442 -> 0.416 ms per iteration, 8 samples 0.838 -> 0.809, 32 samples 3.382 -> 3.355; profiles/README.md)
@@ -1037,7 +1043,7 @@ struct FieldEngine : Engine {
         ws_r.ensure(vb); ws_p.ensure(vb); ws_t.ensure(vb);
         cgws.ensure(nvec);
         const long long itmax = o.maxiters > 0 ? o.maxiters : N;
-        const bool defer = (defer_force || (defer_on && ndim == 2 && dims[0] >= 1024)) && (N & 1) == 0;
+        const bool defer = (defer_force || (defer_on && ndim == 2 && dims[0] >= 1024)) && !big && ndim >= 2 && (N & 1) == 0;
         cgws.defer = defer;
         if (defer) {
             ws_p2.ensure(vb);
@@ -1052,7 +1058,7 @@ struct FieldEngine : Engine {
         { int a, b; tiled_weight(w.as<double>(), nvec, a, b); }      // the shared re-laid weight, before the streams fork
         rt_event_record(ctx->ev0, ctx->stream);
         const CgScalars sc_all = cgws.scalars(o.abstol, o.reltol, itmax, CG_KRYLOV);
-        const int nA = (nvec + 1) / 2;
+        const int nA = (ndim == 1) ? 2 * ((nvec / 2 + 1) / 2) : (nvec + 1) / 2;      // 1-D: whole pairs per group
         for (int g = 0; g < 2; ++g) {
             CgGroup& G = grp[g];
             G.off = g ? nA : 0; G.n = g ? nvec - nA : nA;
@@ -1065,8 +1071,8 @@ struct FieldEngine : Engine {
             rt_stream_wait(G.st, ctx->ev0);
         }
         rt_stream main = ctx->stream;
-        auto enter = [&](CgGroup& G) { ctx->stream = G.st; std::swap(rws, G.rws); std::swap(ws_tile, G.tile); };
-        auto leave = [&](CgGroup& G) { std::swap(rws, G.rws); std::swap(ws_tile, G.tile); ctx->stream = main; };
+        auto enter = [&](CgGroup& G) { ctx->stream = G.st; std::swap(rws, G.rws); std::swap(ws_tile, G.tile); std::swap(cs, G.cs); };
+        auto leave = [&](CgGroup& G) { std::swap(rws, G.rws); std::swap(ws_tile, G.tile); std::swap(cs, G.cs); ctx->stream = main; };
         auto vecs = [&](CgGroup& G, DevBuf& b) { return b.as<double>() + (size_t)G.off * N; };
         auto launch_iter = [&](CgGroup& G, bool first, long long k) {
             FieldPassParams P = base_params();

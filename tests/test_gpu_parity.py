@@ -157,7 +157,8 @@ def test_deferred_solution_update_bitwise(pkg, gpu_ctx, monkeypatch, dims):
     assert len(set(out["1"][0][1].tolist())) >= 3
 
 
-@pytest.mark.parametrize("dims,n", [((2048, 64), 4), ((256, 256), 5), ((32, 64, 16), 3), ((1024, 1024), 2), ((64, 64), 7)])
+@pytest.mark.parametrize("dims,n", [((2048, 64), 4), ((256, 256), 5), ((32, 64, 16), 3), ((1024, 1024), 2), ((64, 64), 7),
+                                    ((65536,), 8), ((4096,), 6), ((8192,), 5), ((256,), 4)])
 def test_two_sample_groups_bitwise(pkg, gpu_ctx, monkeypatch, dims, n):
     """Few samples per GPU: the batched CG runs as two independent lock-step solves on two streams
     (field_engine.cu: sample_cg_grouped).  Same kernels, same per-sample arithmetic: residuals, iteration counts
