@@ -365,6 +365,15 @@ def test_longest_power_of_two_axes(pkg, emu_ctx, dims):
     m.close()
 
 
+@pytest.mark.parametrize("dims", [(5000,), (4097, 8), (8, 8200), (16384, 16)])
+def test_unsupported_axis_lengths_fail_loudly(pkg, emu_ctx, dims):
+    """Beyond the documented limits (include/mgvi_b200.h: any length <= 4096, powers of two <= 8192 in 2-D / 3-D,
+    1-D powers of two <= 2^24) model creation raises -- no silent slow path, no CPU fallback."""
+    cfg = _field(pkg, dims, "LIKE_POISSON", 1)
+    with pytest.raises(pkg.MGVIB200Error, match="axis length"):
+        pkg.model_from_config(cfg, emu_ctx)
+
+
 def test_bluestein_converged_partner_is_masked(pkg, emu_ctx):
     """Two residual samples of a 1-D any-length field share one complex transform.  Once one of them has
     converged its line must leave the transform (a stale line is transformed over and over, grows by ~1e6 per
