@@ -131,7 +131,9 @@ struct FieldEngine : Engine {
     // MGVIB200_PERSIST=1: one persistent cooperative kernel per solve for L2-resident long 1-D fields.  Measured on
     // B200 (profiles/README.md, round 2): C2 0.0599 ms per iteration against 0.0491 ms for the CUDA-graph replay of the
     // stand-alone kernels -- the four phases inlined into one kernel spill ~700 bytes at 128 registers while each
-    // stand-alone kernel fits, which costs more than the three kernel boundaries it saves.  Off by default.
+    // stand-alone kernel fits, which costs more than the three kernel boundaries it saves.  Off by default; it also needs
+    // the 256-thread block size of the four-step kernels (MGVIB200_BIG_THREADS=256; the default is 64).  With one block per
+    // SM at 255 registers (still 288 B of spill) it runs at 0.081 ms.
     bool persist_on = false;
     DevBuf pbar, pparams;           // grid barrier counter and parameter block of the persistent kernel
     CgScalars ncg_sc;
