@@ -45,12 +45,10 @@ SIMT_DEVICE long long big_logical(const BigParams& B, long long pix) {
     return r + (c << B.lg_n1);
 }
 
-// `vbid` >= 0: the block index to act as (persistent kernel: a resident block walks over the block indices of
-// a phase); -1: the hardware block index.
 template <int KIND, int PRO, int EPI>
-SIMT_DEVICE void big1d_body(const BigParams& B, unsigned char* smem_raw, long long vbid = -1) {
+SIMT_DEVICE void big1d_body(const BigParams& B, unsigned char* smem_raw) {
     const FieldPassParams& P = B.f;
-    const long long BID = vbid >= 0 ? vbid : SIMT_BID;
+    const long long BID = SIMT_BID;
     const int lg_len = (KIND == BIG_A || KIND == BIG_AP) ? B.lg_n1 : B.lg_n2;     // transform length of this kernel
     const int n8 = 1 << (lg_len - 3);
     const int lgL = B.lgL;

@@ -188,9 +188,6 @@ void vec_cg_update(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double*
 // deferred solution update (field_pass.h: defer_x): the residual half of the update; the flush of what is still pending
 void vec_cg_update_r(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* r, const double* Ap, long long N, int nvec);
 void vec_x_flush(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* x, const double* p, long long N, int nvec);
-// the same update as kernel parameters + block count, for kernels that run it as one of their phases
-VecParams vec_cg_update_params(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* x, double* r,
-                               const double* p, const double* Ap, long long N, int nvec, long long* grid);
 
 }  // namespace mgvi
 

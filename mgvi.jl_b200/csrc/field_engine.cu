@@ -128,14 +128,6 @@ struct FieldEngine : Engine {
     int groups_mode = -1;             // MGVIB200_GROUPS: -1 auto (few waves per kernel), 1 never, 2 always (2-D / 3-D fast path)
     int big_block_threads = 64;     // (measured at C2: 64 -> 0.0475 ms per iteration, 256 -> 0.0490) MGVIB200_BIG_THREADS: target block size of the four-step kernels (units per block = this / unit size)
     int big_ap_lgL = 3;             // MGVIB200_BIG_AP_LGL: log2(lines per unit) of the column kernel A' (1 = one column pair)
-    // MGVIB200_PERSIST=1: one persistent cooperative kernel per solve for L2-resident long 1-D fields.  Measured on
-    // B200 (profiles/README.md, round 2): C2 0.0599 ms per iteration against 0.0491 ms for the CUDA-graph replay of the
-    // stand-alone kernels -- the four phases inlined into one kernel spill ~700 bytes at 128 registers while each
-    // stand-alone kernel fits, which costs more than the three kernel boundaries it saves.  Off by default; it also needs
-    // the 256-thread block size of the four-step kernels (MGVIB200_BIG_THREADS=256; the default is 64).  With one block per
-    // SM at 255 registers (still 288 B of spill) it runs at 0.081 ms.
-    bool persist_on = false;
-    DevBuf pbar, pparams;           // grid barrier counter and parameter block of the persistent kernel
     CgScalars ncg_sc;
     bool ncg_first = true;
     int h_ncg[2] = {0, 0};
@@ -150,7 +142,7 @@ struct FieldEngine : Engine {
         dense_chol_destroy(chol);
         Mdense.release(); eye.release();
         DevBuf* all[] = {&A, &data, &w, &q, &wbar, &center, &w_tiled, &ws_tile, &ws_r, &ws_p, &ws_p2, &ws_t, &pt_t, &gather, &sc_gather, &kl_red, &qsum, &n_x, &n_r,
-                         &n_p, &n_t, &tmpA, &tmpB, &pbar, &pparams, &cs, &tlo, &thi, &data_perm, &rws.partials, &rws.counters, &rws.red};
+                         &n_p, &n_t, &tmpA, &tmpB, &cs, &tlo, &thi, &data_perm, &rws.partials, &rws.counters, &rws.red};
         for (auto* b : all) b->release();
         for (auto& kv : tw) kv.second.release();
         for (auto& kv : twp) kv.second.release();
@@ -291,7 +283,6 @@ struct FieldEngine : Engine {
         if (const char* e = getenv("MGVIB200_TILED")) tiled_mode = atoi(e);
         if (const char* e = getenv("MGVIB200_GRAPH")) graphs_on = atoi(e) != 0;
         if (const char* e = getenv("MGVIB200_PF")) use_paired = atoi(e) != 0;
-        if (const char* e = getenv("MGVIB200_PERSIST")) persist_on = atoi(e) != 0;
         if (const char* e = getenv("MGVIB200_GROUPS")) groups_mode = atoi(e);
         if (const char* e = getenv("MGVIB200_DEFER_X")) { defer_on = atoi(e) != 0; defer_force = defer_on; if (atoi(e) > 0) defer_mode = std::min(2, atoi(e)); }
         if (const char* e = getenv("MGVIB200_BLUE_MIN")) kBlueMinAxis = std::max<long long>(1, atoll(e));
@@ -946,7 +937,6 @@ struct FieldEngine : Engine {
         if (h[0] > 0 && itmax > 0) {
             launch_iter(true, 0);
             it = 1;
-            if (it < itmax && sample_cg_persistent(sc, R, nvec, itmax - 1)) it = itmax;
             const bool use_graph = rt_has_graphs && graphs_on && !ctx->profile && it < itmax;
             if (use_graph) {
                 // (the first, host-launched iteration above has already sized every buffer for this nvec)
@@ -970,7 +960,7 @@ struct FieldEngine : Engine {
                 }
             }
             if (it >= itmax) {
-                // all remaining iterations ran inside the persistent kernel
+                // a single iteration was asked for
             } else if (!use_graph) {
                 // host-launched iterations (emulator build, per-kernel profiling, MGVIB200_GRAPH=0): poll after
                 // 1, 2, 4, 8, 8, ... iterations
@@ -1193,59 +1183,6 @@ struct FieldEngine : Engine {
             mx = std::max<long long>(mx, hi[i]);
         }
         ctx->lockstep_iters = mx;
-    }
-
-    // Long 1-D fields whose CG state stays in L2 (C2): every iteration after the first in ONE cooperative launch
-    // (kernels.h: k_big1d_cg_persist).  Returns false when the shape does not qualify; the caller then runs the
-    // graph / host-launched sequence.  Same kernels bodies, same launch geometry per phase, same results.
-    bool sample_cg_persistent(const CgScalars& sc, double* R, int nvec, long long max_iters) {
-#if defined(__CUDACC__) && !defined(MGVI_SIMT_EMU)
-        if (!big || !rt_has_coop || !persist_on || ctx->profile) return false;
-        if ((size_t)N * nvec * sizeof(double) > ((size_t)32 << 20)) return false;
-        BigCgParams Q;
-        memset(&Q, 0, sizeof Q);
-        size_t smem = 512;
-        bool ok = true;
-        for (int pass = 0; pass < 2; ++pass) {         // second pass: the reduction workspace no longer moves
-            FieldPassParams P = base_params();
-            P.r = ws_r.as<double>(); P.p = ws_p.as<double>();
-            P.vin = ws_p.as<double>(); P.vin_ld = N;
-            P.out = ws_t.as<double>(); P.out_ld = N;
-            P.w = w.as<double>();
-            P.first_iter = 0;
-            P.cg = sc;
-            P.mask_active = 1;
-            P.scale = c * c * pow(0.5, 2 * ndim);
-            FieldPassParams E = P;
-            E.fin = FIN_CG_PAP; E.red_out = nullptr;
-            P.fin = FIN_NONE;
-            const BigLaunch a = prep_big<BIG_A>(P, nvec), b = prep_big<BIG_B_MID>(P, nvec), ap = prep_big<BIG_AP>(E, nvec);
-            Q.a = a.B; Q.b = b.B; Q.ap = ap.B;
-            Q.grid_a = a.grid; Q.grid_b = b.grid; Q.grid_ap = ap.grid;
-            Q.u = vec_cg_update_params(ctx, rws, sc, R, ws_r.as<double>(), ws_p.as<double>(), ws_t.as<double>(), N, nvec, &Q.grid_u);
-            ok = (a.threads == 256 && b.threads == 256 && ap.threads == 256);
-            smem = std::max(std::max(a.smem, b.smem), std::max(ap.smem, (size_t)512));
-        }
-        if (!ok) return false;
-        const long long cap = rt_max_coresident(k_big1d_cg_persist<0>, 256, smem);
-        if (cap < ctx->sm_count) return false;
-        const long long want = std::max(std::max(Q.grid_a, Q.grid_b), std::max(Q.grid_ap, Q.grid_u));
-        const long long grid = std::min(want, cap);
-        pbar.ensure(64);
-        rt_memset(pbar.p, 0, 64, ctx->stream);
-        Q.bar = pbar.as<unsigned>();
-        Q.max_iters = max_iters;
-        pparams.ensure(sizeof Q);
-        rt_h2d(pparams.p, &Q, sizeof Q, ctx->stream);
-        rt_sync(ctx->stream);                 // Q is a stack object
-        const BigCgParams* Qd = pparams.as<BigCgParams>();
-        rt_launch_coop(k_big1d_cg_persist<0>, grid, 256, smem, ctx->stream, Qd);
-        ctx->launches++;
-        return true;
-#else
-        (void)sc; (void)R; (void)nvec; (void)max_iters;
-        return false;
-#endif
     }
 
     // MatrixInversion (src/residual_samplers.jl:95-123): the reference materialises M = J'FJ + I by n_theta

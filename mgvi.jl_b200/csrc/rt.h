@@ -102,26 +102,6 @@ inline void rt_launch_pdl(K kernel, long long grid, int block, size_t smem, rt_s
     RT_CUDA(cudaLaunchKernelEx(&cfg, kernel, params));
 }
 
-// Cooperative launch (all blocks co-resident: kernels with grid-wide barriers) and the number of blocks of a
-// kernel one device can hold at once
-static const bool rt_has_coop = true;
-template <typename K>
-inline long long rt_max_coresident(K kernel, int block, size_t smem) {
-    if (smem > 48 * 1024) rt_ensure_smem_attr((const void*)kernel, smem);
-    int per_sm = 0, dev = 0, sms = 0, coop = 0;
-    RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
-    RT_CUDA(cudaGetDevice(&dev));
-    RT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    RT_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-    return coop ? (long long)per_sm * sms : 0;
-}
-template <typename K, typename P>
-inline void rt_launch_coop(K kernel, long long grid, int block, size_t smem, rt_stream s, const P& params) {
-    if (smem > 48 * 1024) rt_ensure_smem_attr((const void*)kernel, smem);
-    void* args[1] = {const_cast<P*>(&params)};
-    RT_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)grid), dim3((unsigned)block), args, smem, s));
-}
-
 // CUDA graphs: a fixed launch sequence (several lock-step CG iterations -- every per-iteration scalar
 // lives in device memory, so the kernel parameters do not change) captured once and replayed
 typedef cudaGraphExec_t rt_graph;
@@ -195,7 +175,6 @@ inline void rt_event_destroy(rt_event) {}
 inline void rt_event_record(rt_event, rt_stream) {}
 inline double rt_event_ms(rt_event, rt_event) { return 0.0; }
 
-static const bool rt_has_coop = false;
 typedef int rt_graph;
 static const bool rt_has_graphs = false;
 inline void rt_capture_begin(rt_stream) {}

@@ -165,19 +165,4 @@ void vec_x_flush(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* x
     vec_launch(ctx, ws, P);
 }
 
-VecParams vec_cg_update_params(mgvib200_ctx* ctx, ReduceWs& ws, const CgScalars& cg, double* x, double* r,
-                               const double* p, const double* Ap, long long N, int nvec, long long* grid) {
-    VecParams P = vp_zero();
-    P.op = VOP_CG_UPDATE; P.N = N; P.nvec = nvec; P.x = x; P.r = r; P.p = p; P.Ap = Ap;
-    P.fin = FIN_CG_RR; P.cg = cg;
-    P.per_block = kVecPerBlock;
-    P.nchunk = (P.N + kVecPerBlock - 1) / kVecPerBlock;
-    *grid = P.nchunk * P.nvec;
-    reduce_ws_ensure(ws, ctx, (size_t)*grid, (size_t)(P.nvec > 1 ? P.nvec : 1));
-    P.partials = ws.partials.as<double>();
-    P.counters = ws.counters.as<unsigned>();
-    P.red_out = ws.red.as<double>();
-    return P;
-}
-
 }  // namespace mgvi

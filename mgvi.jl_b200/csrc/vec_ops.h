@@ -102,11 +102,10 @@ SIMT_DEVICE void vec_elem(const VecParams& P, int s, long long i, double alpha, 
 }
 
 // block -> (chunk, vector); a block covers `per_block` consecutive elements of one vector.
-// `vbid` >= 0: the block index to act as (persistent kernels); -1: the hardware block index.
-SIMT_DEVICE void vec_body(const VecParams& P, unsigned char* smem_raw, long long vbid = -1) {
+SIMT_DEVICE void vec_body(const VecParams& P, unsigned char* smem_raw) {
     double* red = reinterpret_cast<double*>(smem_raw);
     int* flag = reinterpret_cast<int*>(smem_raw + 256);
-    const long long BID = vbid >= 0 ? vbid : SIMT_BID;
+    const long long BID = SIMT_BID;
     const int s = (int)(BID % P.nvec);
     const long long chunk = BID / P.nvec;
     const bool cg_op = (P.op == VOP_CG_UPDATE || P.op == VOP_CG_PUPD || P.op == VOP_CG_PAP || P.op == VOP_CG_UPDATE_R);
